@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of MaGNet's multi-view matching hot path on B200 (BASELINE.json metric).
+
+One *step* = one pass of the hot path over one batch of synthetic frames per GPU:
+    source repack (NCHW -> C4HW4) + camera table  [once per batch, inside the timed region]
+    N_iter = 3 x ( fused sampler + warp + bilinear sample + consistency + view fusion kernel
+                   -> Gaussian update kernel on a fixed synthetic G-Net output )
+A *frame* is one reference image's full matching loop (SURVEY §8 d).  Workload at N=1 is BASELINE.json
+configs[1]: 640x480 (quarter-res grid 120x160), 4 source views, 64 hypotheses, batch 8 per GPU; N>1 is weak
+scaling (each rank owns its own batch of 8; the path has no data-path collective, SURVEY §8 e).
+
+  value     whole-job frames/s, inputs resident in HBM, device-timed (CUDA events), max over ranks
+  e2e       same loop through the reference-facing drop-in API (sample_depths + est_costvolume_CW +
+            gaussian_update) with pinned HOST buffers: H2D of every input and D2H of the result inside the
+            timed region
+  roofline  dominant kernel (cost volume): algorithmic bytes / its CUDA-event duration vs measured HBM peak
+  cpu_baseline / --impl reference
+            the reference's CPU path (its ATen operator sequence, oracle/torch_ref.py — /root/reference is a
+            Python repo and cannot travel) timed on this box's host cores on a bounded sample (1-frame batches)
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "frames/sec (640x480, 4 views, 64 hyp)"
+N_ITER = 3
+WORKLOADS = {
+    "cfg2": "scannet-640x480(q120x160)-V4-D64-B8",
+    "cfg3": "kitti-1216x352(q88x304)-V4-D64-B4",
+}
+
+
+def algorithmic_bytes(B, V, D, C, HW, fused=True):
+    """every tensor read or written once, fp32.  S = 2 (mu, sigma) when the sampler is fused,
+    D when d_volume is read."""
+    S = 2 if fused else D
+    return 4 * B * HW * (C + V * C + 2 * V + 3 + S + D)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload):
+    """DRAM bytes per launch of the cost kernel from the committed ncu capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons DURING the timed region (pynvml; nvidia-smi as a fallback)."""
+
+    def __init__(self, index=0, period=0.004):
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
+
+    def _decode(self, mask):
+        n = self._nvml
+        names = {
+            "hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(n, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        return {k for k, bit in names.items() if mask & bit}
+
+    def _loop(self):
+        n = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
+                try:
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                self.reasons |= self._decode(mask)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def start(self):
+        if self._nvml is not None:
+            self._stop.clear()
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+            self._thr = None
+
+    def report(self):
+        if self._nvml is None:
+            try:
+                import subprocess
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=10).stdout
+                cur, mx = [float(x) for x in out.strip().split(",")]
+                return {"sm_mhz": cur, "sm_max_mhz": mx, "reasons": [], "samples": 1, "how": "nvidia-smi after the timed region"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "how": "unavailable"}
+        s = sorted(self.samples)
+        med = s[len(s) // 2] if s else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s),
+                "how": "pynvml, %.0f ms period, during the timed region(s)" % (self.period * 1e3)}
+
+
+def cpu_reference_frames(frames_cfg, steps, warmup, threads=None, budget_s=None):
+    """Time the reference's CPU operator sequence (oracle/torch_ref.py: sampler -> est_costvolume_CW ->
+    Gaussian update, N_ITER iterations) on 1-frame batches of the same workload.  Returns (frames/s, info)."""
+    from magnet_b200.synthetic import make_config
+    from oracle import torch_ref
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    inp = make_config(frames_cfg, seed=1, B=1)
+    klist = [float(v) for v in inp.k.tolist()]
+    g = torch.Generator().manual_seed(5)
+    raw = torch.randn(1, 2, *inp.ref_feat.shape[2:], generator=g) * 0.1
+
+    def one_frame():
+        pred = inp.ref_gmms
+        for _ in range(N_ITER):
+            dvol = torch_ref.sample_depth_candidates(pred, klist)
+            torch_ref.cost_volume_cw(dvol, inp.ref_feat, inp.nghbr_feat, inp.ref_gmms, inp.nghbr_gmms, inp.R, inp.t,
+                                     inp.is_valid, inp.cam_intrins, inp.thres)
+            pred = torch_ref.gaussian_update(raw, pred)
+        return pred
+
+    with torch.no_grad():
+        for _ in range(warmup):
+            one_frame()
+        t0 = time.perf_counter()
+        done = 0
+        for _ in range(steps):
+            one_frame()
+            done += 1
+            if budget_s is not None and time.perf_counter() - t0 > budget_s:
+                break
+        dt = time.perf_counter() - t0
+    info = {"cores": cores, "os_cpu_count": os.cpu_count(), "frames": done, "seconds": dt,
+            "sample": f"{done} x 1-frame batch of {WORKLOADS[frames_cfg]} (B=1), {N_ITER} iterations each, "
+                      f"ATen port of the reference operator sequence, {cores} threads"}
+    return done / dt, info
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    fps, info = cpu_reference_frames(args.config, max(1, args.steps), max(0, min(args.warmup, 1)), budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": info["frames"], "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * info["seconds"] / max(1, info["frames"]),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.config], "n_iter": N_ITER, "device": "host CPU"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--variant", default="auto", choices=["auto", "direct", "cells"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gnet", action="store_true")
+    args = ap.parse_args()
+
+    from magnet_b200 import dist as md
+    rank, local_rank, world = md.env_world()
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: magnet_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    md.init_process_group("nccl")
+    K, W = max(1, args.steps), max(3, args.warmup)
+
+    import magnet_b200
+    from magnet_b200 import _lib, ops
+    from magnet_b200.synthetic import make_config
+    variant = {"auto": _lib.VARIANT_AUTO, "direct": _lib.VARIANT_DIRECT, "cells": _lib.VARIANT_CELLS}[args.variant]
+
+    inp = make_config(args.config, seed=1 + rank)
+    B, V, D = inp.B, inp.V, inp.D
+    C, H, Wd = inp.ref_feat.shape[1], inp.ref_feat.shape[2], inp.ref_feat.shape[3]
+    HW = H * Wd
+    g = inp.to(dev)
+    klist = [float(v) for v in inp.k.tolist()]
+    karr = ops.k_array(klist)
+    gen = torch.Generator().manual_seed(5 + rank)
+    raw = (torch.randn(B, 2, H, Wd, generator=gen) * 0.1).to(dev)     # stand-in G-Net output (fixed)
+    is_valid_d = inp.is_valid.to(dev)
+    intM_d = inp.cam_intrins['intM'].to(dev)
+    rays_d = inp.cam_intrins['unit_ray_array_2D'].to(dev).contiguous()
+    src_packed = torch.empty(V * B, C // 4, H, Wd, 4, device=dev)
+    cv = torch.empty(B, D, H, Wd, device=dev)
+    ev_pairs = []
+
+    def hot_step(record=False):
+        """repack + camera table + N_ITER x (fused cost kernel -> update kernel); everything device-resident."""
+        ops.repack_c4hw4(g.nghbr_feat, out=src_packed)
+        cams = ops.pack_cameras(intM_d, g.R, g.t, is_valid_d)
+        pred = g.ref_gmms
+        for _ in range(N_ITER):
+            if record:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            ops.cost_volume(g.ref_feat, src_packed, rays_d, cams, V=V, src_layout=_lib.SRC_C4HW4, consistency=True,
+                            src_gmm=g.nghbr_gmms, kappa=float(inp.thres), ref_gmm=pred, k=karr, out=cv, variant=variant)
+            if record:
+                e1.record()
+                ev_pairs.append((e0, e1))
+            pred = ops.gaussian_update(raw, pred)
+        return pred
+
+    def timed(fn, steps, sampler=None):
+        md.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.stop()
+        md.barrier()
+        return md.max_over_ranks(s.elapsed_time(e), device=dev)
+
+    sampler = ClockSampler(index=local_rank) if rank == 0 else None
+    with torch.no_grad():
+        for _ in range(W):
+            hot_step()
+        l0 = _lib.launch_count()
+        ms_total = timed(lambda: hot_step(record=True), K, sampler)
+        launches = _lib.launch_count() - l0
+    ms_step = ms_total / K
+    frames_per_s = world * B * 1e3 / ms_step
+    kern_ms = sum(a.elapsed_time(b) for a, b in ev_pairs) / max(1, len(ev_pairs))
+    if sampler and len(sampler.samples) < 5:
+        # timed region too short for the sampler: keep the identical load running while sampling
+        with torch.no_grad():
+            sampler.start()
+            t_end = time.time() + 1.0
+            while time.time() < t_end:
+                hot_step()
+            torch.cuda.synchronize()
+            sampler.stop()
+
+    # ---- loop including the real G-Net convolutions (PyTorch / cuDNN), reported beside the headline --------
+    with_gnet = None
+    if not args.no_gnet:
+        torch.manual_seed(0)
+        head = magnet_b200.GNET(ch_in=256 + D).to(dev).eval()
+        x_d3 = torch.randn(B, 256, H, Wd, device=dev)
+
+        def gnet_step():
+            plan = magnet_b200.MatchingPlan(g.ref_feat, g.nghbr_feat, g.nghbr_gmms, g.nghbr_poses, is_valid_d,
+                                            {"intM": intM_d, "unit_ray_array_2D": rays_d}, thres=inp.thres)
+            return magnet_b200.matching_loop(plan, g.ref_gmms, x_d3, head.gnet, N_ITER, karr, variant=variant)[-1]
+
+        with torch.no_grad():
+            for _ in range(3):
+                gnet_step()
+            kg = max(3, K // 10)
+            ms_g = timed(gnet_step, kg) / kg
+        with_gnet = {"value": world * B * 1e3 / ms_g, "unit": "frames/s", "ms_per_step": ms_g,
+                     "note": "same loop + G-Net conv head (cuDNN, fp32) on a random 256-ch D-Net feature"}
+
+    # ---- e2e: drop-in API, pinned host buffers, H2D + D2H inside the timed region ---------------------------
+    host = {k: getattr(inp, k).contiguous().pin_memory() for k in ("ref_feat", "nghbr_feat", "ref_gmms", "nghbr_gmms", "nghbr_poses")}
+    out_host = torch.empty(B, 2, H, Wd).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in host.values())
+    d2h = out_host.numel() * out_host.element_size()
+
+    def e2e_step():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        R, t = d["nghbr_poses"][:, :, :3, :3], d["nghbr_poses"][:, :, :3, 3]
+        pred = d["ref_gmms"]
+        for _ in range(N_ITER):
+            dvol = ops.sample_depths(pred, karr)
+            cvol = magnet_b200.est_costvolume_CW(dvol, d["ref_feat"], d["nghbr_feat"], d["ref_gmms"], d["nghbr_gmms"],
+                                                 R, t, inp.is_valid, inp.cam_intrins, inp.thres, variant=variant)
+            pred = ops.gaussian_update(raw, pred)
+        out_host.copy_(pred, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller reads the result on the host
+        return cvol
+
+    with torch.no_grad():
+        for _ in range(3):
+            e2e_step()
+        ke = max(3, K // 10)
+        ms_e = timed(e2e_step, ke) / ke
+    e2e = {"value": world * B * 1e3 / ms_e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": ms_e, "api": "sample_depths + est_costvolume_CW (drop-in, d_volume mode) + gaussian_update",
+           "steps": ke}
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    abytes = algorithmic_bytes(B, V, D, C, HW, fused=True)
+    achieved = abytes / (kern_ms * 1e-3) / 1e9
+    grid, block, smem = ops.cost_launch_info(B, V, D, C, H, Wd, variant=variant)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(args.config), "kernel": "cost_cells_kernel<64,GAUSS,C4HW4,CW>" if variant != _lib.VARIANT_DIRECT else "cost_direct_kernel<CW>",
+                "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src,
+                "launch": {"grid": grid, "block": block, "smem_bytes": smem}}
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        fps, info = cpu_reference_frames(args.config, steps=8, warmup=1, budget_s=20.0)
+        cpu_baseline = {"value": fps, "unit": "frames/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]}
+    line = {
+        "metric": METRIC, "value": frames_per_s, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.config], "frames_per_step_per_gpu": B, "n_iter": N_ITER, "views": V,
+                   "hypotheses": D, "channels": C, "grid": [H, Wd], "depth": inp.meta["depth"], "variant": args.variant,
+                   "cache": "inputs_larger_than_l2 (%.0f MB resident per step vs 126 MB L2)" % ((abytes + 4 * V * B * C * HW) / 1e6),
+                   "step": "repack + camera table + %d x (fused cost kernel + update kernel)" % N_ITER},
+        "clocks": sampler.report() if sampler else None,
+        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "with_gnet": with_gnet,
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

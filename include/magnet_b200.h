@@ -1,0 +1,148 @@
+/*
+ * magnet_b200.h — C ABI of the B200-native multi-view matching hot path of MaGNet.
+ *
+ * The reference (baegwangbin/MaGNet) has no FFI layer: its boundary is two Python
+ * module-level functions and two inlined blocks (SURVEY §8 b).  Every entry point
+ * below names the reference interface it replaces.  A maintainer binds these with
+ * ctypes / cffi / pybind; magnet_b200/_lib.py is such a binding.
+ *
+ * Conventions
+ *   - plain C, no torch types; every pointer is a DEVICE pointer unless the field says
+ *     "host"; all tensors are fp32, dense, in the layout stated per field;
+ *   - caller owns all memory; no entry point allocates, frees or synchronises; every
+ *     launch goes to the cudaStream_t passed as `stream` (NULL = legacy default
+ *     stream), so calls are CUDA-graph capturable;
+ *   - re-entrant and stateless (one-time cudaFuncSetAttribute calls are idempotent);
+ *   - return value: MAGNET_OK (0) or a negative magnet_status; never throws.
+ */
+#ifndef MAGNET_B200_H_
+#define MAGNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAGNET_ABI_VERSION 1
+#define MAGNET_MAX_PLANES 256   /* max depth hypotheses / planes per call (D) */
+
+typedef enum magnet_status {
+  MAGNET_OK = 0,
+  MAGNET_ERR_NULL = -1,        /* a required pointer is NULL */
+  MAGNET_ERR_SHAPE = -2,       /* a dimension is <= 0 or inconsistent */
+  MAGNET_ERR_UNSUPPORTED = -3, /* C, D, layout or variant not supported by this build */
+  MAGNET_ERR_CUDA = -4,        /* a CUDA runtime call failed (see magnet_last_cuda_error) */
+  MAGNET_ERR_ALIGN = -5        /* a pointer violates the required 16-byte alignment */
+} magnet_status;
+
+/* Where the per-pixel depth hypotheses come from. */
+typedef enum magnet_depth_mode {
+  MAGNET_DEPTH_VOLUME = 0, /* read d_volume (B,D,H,W): drop-in for est_costvolume_CW         */
+  MAGNET_DEPTH_GAUSS = 1,  /* d_j = mu + sigma*k_j from ref_gmm + k: sampler fused            */
+  MAGNET_DEPTH_PLANES = 2  /* d_j = k_j for every pixel: fronto-parallel planes (est_costvolume_F) */
+} magnet_depth_mode;
+
+/* Memory layout of the source-view feature maps. */
+typedef enum magnet_src_layout {
+  MAGNET_SRC_NCHW = 0,  /* (V*B, C, H, W), the reference layout                                */
+  MAGNET_SRC_C4HW4 = 1  /* (V*B, C/4, H, W, 4): channel quads innermost, see magnet_repack_c4hw4_f32 */
+} magnet_src_layout;
+
+/* Kernel selection (for parity cross-checks and profiling). */
+typedef enum magnet_variant {
+  MAGNET_VARIANT_AUTO = 0,   /* production choice                                              */
+  MAGNET_VARIANT_DIRECT = 1, /* one thread per output, 4 taps x C channels per hypothesis,
+                                reference operation order, fp64 view accumulation             */
+  MAGNET_VARIANT_CELLS = 2   /* tap-sharing kernel: per-lane bilinear-cell records             */
+} magnet_variant;
+
+/* Per (batch element, view) camera constants, 16 floats, produced by magnet_pack_cameras_f32.
+ * index = b*V + v.  Replaces the per-pair matmuls at homography.py:98-102. */
+typedef struct magnet_camera {
+  float valid;  /* 1.0f when is_valid[b,v] == 1, else 0.0f (homography.py:97)                  */
+  float a[3];   /* K_b * t_bv          ('term1_pix', homography.py:101)                        */
+  float A[9];   /* K_b * R_bv row-major; A*ray = 'term2_pix' (homography.py:102).  Row 2 equals
+                   R_bv[2,:] and a[2] equals t_bv[2], i.e. the z rows of 'term1_cam/term2_cam' */
+  float pad[3];
+} magnet_camera;
+
+/*
+ * Arguments of the fused warp + bilinear sample + consistency weight + view fusion kernel.
+ * Replaces models/submodules/homography.py:79-161 (est_costvolume_CW + _compute_cost_CW) and,
+ * with consistency == 0, homography.py:10-75 (est_costvolume_F + _compute_cost_F);
+ * with depth_mode == MAGNET_DEPTH_GAUSS it also absorbs the sampler of models/MAGNET.py:154-156.
+ */
+typedef struct magnet_cost_args {
+  int32_t B, V, D, C, H, W;
+  int32_t depth_mode;      /* magnet_depth_mode                                                 */
+  int32_t src_layout;      /* magnet_src_layout                                                 */
+  int32_t consistency;     /* 1: CW weighting |z - mu~| < kappa*sigma~ ; 0: plain plane sweep   */
+  int32_t softmax;         /* 1: softmax over the D planes after the 1/V mean (est_costvolume_F)*/
+  int32_t variant;         /* magnet_variant                                                    */
+  float kappa;             /* 'thres' of est_costvolume_CW (float(int))                         */
+  const float* ref_feat;   /* (B, C, H, W) NCHW                                                 */
+  const float* src_feat;   /* (V*B, ...) view-major, layout = src_layout                        */
+  const float* src_gmm;    /* (V*B, 2, H, W) [mu, sigma]; required when consistency == 1        */
+  const float* rays;       /* (B, 3, H*W) 'unit_ray_array_2D'                                   */
+  const magnet_camera* cams; /* (B*V)                                                           */
+  const float* d_volume;   /* (B, D, H, W); MAGNET_DEPTH_VOLUME only                            */
+  const float* ref_gmm;    /* (B, 2, H, W) [mu, sigma]; MAGNET_DEPTH_GAUSS only                 */
+  const float* k_host;     /* HOST pointer, D floats: k_j (GAUSS) or plane depths (PLANES)      */
+  float* out;              /* (B, D, H, W)                                                      */
+} magnet_cost_args;
+
+int magnet_abi_version(void);
+const char* magnet_strerror(int status);
+/* Text of the last CUDA error seen by this library on the calling thread ("" if none). */
+const char* magnet_last_cuda_error(void);
+/* Number of kernels this library has launched so far in this process (all entry points). */
+uint64_t magnet_launch_count(void);
+
+/* Bytes of dynamic shared memory and threads per CTA the selected variant will use (for reports). */
+int magnet_cost_launch_info(const magnet_cost_args* args, int* grid_ctas, int* block_threads, int* smem_bytes);
+
+/* Cost volume, forward.  Replaces homography.est_costvolume_CW / est_costvolume_F (see above). */
+int magnet_cost_volume_f32(const magnet_cost_args* args, void* stream);
+
+/*
+ * Camera constants.  Replaces homography.py:89,98-102 (IntM/R/t products, done there per pair per
+ * iteration).  intM (B,3,3) dense; R and t are addressed with element strides so that the
+ * non-contiguous views nghbr_poses[:,:,:3,:3] / [:,:,:3,3] of MAGNET.py:147-148 can be passed as is:
+ *   R[b,v,i,j] = R[b*r_sb + v*r_sv + i*r_si + j*r_sj],  t[b,v,i] = t[b*t_sb + v*t_sv + i*t_si].
+ * is_valid (B,V) int32 on the device.
+ */
+int magnet_pack_cameras_f32(const float* intM, const float* R, int64_t r_sb, int64_t r_sv, int64_t r_si,
+                            int64_t r_sj, const float* t, int64_t t_sb, int64_t t_sv, int64_t t_si,
+                            const int32_t* is_valid, int32_t B, int32_t V, magnet_camera* cams_out,
+                            void* stream);
+
+/* Source-feature repack (N, C, H, W) -> (N, C/4, H, W, 4); C % 4 == 0, dst 16-byte aligned. */
+int magnet_repack_c4hw4_f32(const float* src_nchw, float* dst, int32_t N, int32_t C, int32_t H, int32_t W,
+                            void* stream);
+
+/*
+ * Depth-candidate sampler alone.  Replaces models/MAGNET.py:154-156:
+ *   d_volume[b,j,y,x] = mu[b,y,x] + sigma[b,y,x] * k_j   (separate multiply and add).
+ * gmm (B,2,H,W); k_host: HOST pointer, D floats; d_volume (B,D,H,W).
+ */
+int magnet_sample_depths_f32(const float* gmm, const float* k_host, int32_t B, int32_t D, int32_t HW,
+                             float* d_volume, void* stream);
+
+/*
+ * Gaussian update, forward.  Replaces models/MAGNET.py:60,65-69 (inside GNET.forward):
+ *   mu' = mu0 + mu1*sigma0 ; sigma' = (elu(sigma1) + 1 + 1e-10) * sigma0.
+ * d_output (B,2,H,W) = G-Net raw output (mu1, sigma1); ref_gmm (B,2,H,W); out (B,2,H,W).
+ */
+int magnet_gaussian_update_fwd_f32(const float* d_output, const float* ref_gmm, int32_t B, int32_t HW,
+                                   float* out, void* stream);
+/* Backward of the update w.r.t. d_output (ref_gmm is detached in the reference, MAGNET.py:168):
+ *   g_mu1 = g_mu' * sigma0 ; g_sigma1 = g_sigma' * sigma0 * (sigma1 > 0 ? 1 : exp(sigma1)). */
+int magnet_gaussian_update_bwd_f32(const float* grad_out, const float* d_output, const float* ref_gmm,
+                                   int32_t B, int32_t HW, float* grad_d_output, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAGNET_B200_H_ */

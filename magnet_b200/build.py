@@ -1,0 +1,72 @@
+"""In-tree build of libmagnet_b200.so (sm_100a) with plain nvcc — no torch extension machinery.
+
+The C-ABI library has no torch dependency, so it is compiled straight from magnet_b200/csrc/*.cu
+into magnet_b200/libmagnet_b200.so; the built file travels to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+BUILD = PKG / "_build"
+LIB = PKG / "libmagnet_b200.so"
+SOURCES = ["api.cu", "cost_cells.cu", "cost_direct.cu", "aux_kernels.cu"]
+HEADERS = [CSRC / "common.cuh", PKG.parent / "include" / "magnet_b200.h"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; cannot build libmagnet_b200.so")
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    for f in [CSRC / s for s in SOURCES] + HEADERS:
+        h.update(f.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every .cu for sm_100a and link the shared library.  No-op when up to date."""
+    BUILD.mkdir(exist_ok=True)
+    stamp = BUILD / "digest.txt"
+    dig = _digest()
+    if not force and LIB.exists() and stamp.exists() and stamp.read_text() == dig:
+        return LIB
+    nvcc = _nvcc()
+
+    def compile_one(src: str):
+        obj = BUILD / (src + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-I", str(PKG.parent / "include"), "-c", str(CSRC / src), "-o", str(obj)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        (BUILD / (src + ".log")).write_text(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            sys.stderr.write(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    stamp.write_text(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

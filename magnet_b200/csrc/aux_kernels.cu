@@ -1,0 +1,126 @@
+// Small kernels around the cost volume: camera constants, source repack, sampler, Gaussian update.
+#include "common.cuh"
+
+namespace magnet {
+
+// homography.py:98-102 — a = K t, A = K R, one thread per (b, v).  fp32, products accumulated in
+// index order (the reference uses a 3x3 fp32 matmul; any order differs by <= 1 ulp).
+__global__ void pack_cameras_kernel(const float* __restrict__ intM, const float* __restrict__ R, int64_t r_sb,
+                                    int64_t r_sv, int64_t r_si, int64_t r_sj, const float* __restrict__ t,
+                                    int64_t t_sb, int64_t t_sv, int64_t t_si,
+                                    const int32_t* __restrict__ is_valid, int B, int V,
+                                    magnet_camera* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * V) return;
+  const int b = idx / V, v = idx % V;
+  const float* K = intM + (size_t)b * 9;
+  const float* Rp = R + b * r_sb + v * r_sv;
+  const float* tp = t + b * t_sb + v * t_sv;
+  magnet_camera c;
+  c.valid = (is_valid[idx] == 1) ? 1.0f : 0.0f;
+  const float t0 = tp[0], t1 = tp[t_si], t2 = tp[2 * t_si];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float k0 = K[i * 3 + 0], k1 = K[i * 3 + 1], k2 = K[i * 3 + 2];
+    c.a[i] = __fmaf_rn(k2, t2, __fmaf_rn(k1, t1, __fmul_rn(k0, t0)));
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      c.A[i * 3 + j] = __fmaf_rn(k2, Rp[2 * r_si + j * r_sj],
+                                 __fmaf_rn(k1, Rp[1 * r_si + j * r_sj], __fmul_rn(k0, Rp[0 * r_si + j * r_sj])));
+  }
+  c.pad[0] = c.pad[1] = c.pad[2] = 0.0f;
+  out[idx] = c;
+}
+
+// (N, C, H, W) -> (N, C/4, H, W, 4).  One thread per (n, c4, pixel): 4 coalesced 4-byte reads
+// (stride HW), one coalesced 16-byte write.
+__global__ void repack_c4hw4_kernel(const float* __restrict__ src, float4* __restrict__ dst, int C4, int HW) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= HW) return;
+  const size_t img = blockIdx.z, c4 = blockIdx.y;
+  const float* s = src + (img * C4 * 4 + c4 * 4) * HW + n;
+  float4 o;
+  o.x = s[0];
+  o.y = s[(size_t)HW];
+  o.z = s[2 * (size_t)HW];
+  o.w = s[3 * (size_t)HW];
+  dst[(img * C4 + c4) * HW + n] = o;
+}
+
+struct KParams {
+  float k[MAGNET_MAX_PLANES];
+};
+
+// MAGNET.py:154-156
+__global__ void sample_depths_kernel(const float* __restrict__ gmm, const __grid_constant__ KParams kp, int D,
+                                     int HW, float* __restrict__ dvol) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= HW) return;
+  const size_t b = blockIdx.y;
+  const float mu = gmm[(b * 2 + 0) * HW + n], sg = gmm[(b * 2 + 1) * HW + n];
+  float* o = dvol + b * D * HW + n;
+  for (int j = 0; j < D; ++j) o[(size_t)j * HW] = __fadd_rn(mu, __fmul_rn(sg, kp.k[j]));
+}
+
+// MAGNET.py:60,65-69.  torch's ELU evaluates exp(x) - 1 on the negative side (not expm1).
+__global__ void gaussian_update_fwd_kernel(const float* __restrict__ dout, const float* __restrict__ gmm0,
+                                           int HW, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= HW) return;
+  const size_t b = blockIdx.y;
+  const float mu1 = dout[(b * 2 + 0) * HW + n], s1 = dout[(b * 2 + 1) * HW + n];
+  const float mu0 = gmm0[(b * 2 + 0) * HW + n], s0 = gmm0[(b * 2 + 1) * HW + n];
+  const float elu = s1 > 0.0f ? s1 : __fsub_rn(expf(s1), 1.0f);
+  out[(b * 2 + 0) * HW + n] = __fadd_rn(mu0, __fmul_rn(mu1, s0));
+  out[(b * 2 + 1) * HW + n] = __fmul_rn(__fadd_rn(__fadd_rn(elu, 1.0f), 1e-10f), s0);
+}
+
+__global__ void gaussian_update_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ dout,
+                                           const float* __restrict__ gmm0, int HW, float* __restrict__ gin) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= HW) return;
+  const size_t b = blockIdx.y;
+  const float s1 = dout[(b * 2 + 1) * HW + n];
+  const float s0 = gmm0[(b * 2 + 1) * HW + n];
+  const float g_mu = gout[(b * 2 + 0) * HW + n], g_sg = gout[(b * 2 + 1) * HW + n];
+  gin[(b * 2 + 0) * HW + n] = __fmul_rn(g_mu, s0);
+  const float delu = s1 > 0.0f ? 1.0f : expf(s1);
+  gin[(b * 2 + 1) * HW + n] = __fmul_rn(__fmul_rn(g_sg, delu), s0);
+}
+
+cudaError_t launch_pack_cameras(const float* intM, const float* R, int64_t r_sb, int64_t r_sv, int64_t r_si,
+                                int64_t r_sj, const float* t, int64_t t_sb, int64_t t_sv, int64_t t_si,
+                                const int32_t* is_valid, int B, int V, magnet_camera* out, cudaStream_t st) {
+  const int n = B * V;
+  pack_cameras_kernel<<<(n + 63) / 64, 64, 0, st>>>(intM, R, r_sb, r_sv, r_si, r_sj, t, t_sb, t_sv, t_si,
+                                                    is_valid, B, V, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_repack(const float* src, float* dst, int N, int C, int H, int W, cudaStream_t st) {
+  const int HW = H * W;
+  dim3 grid((HW + 255) / 256, C / 4, N);
+  repack_c4hw4_kernel<<<grid, 256, 0, st>>>(src, reinterpret_cast<float4*>(dst), C / 4, HW);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sample(const float* gmm, const float* k_host, int B, int D, int HW, float* dvol,
+                          cudaStream_t st) {
+  KParams kp;
+  for (int j = 0; j < MAGNET_MAX_PLANES; ++j) kp.k[j] = j < D ? k_host[j] : 0.0f;
+  sample_depths_kernel<<<dim3((HW + 255) / 256, B), 256, 0, st>>>(gmm, kp, D, HW, dvol);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_update_fwd(const float* dout, const float* gmm0, int B, int HW, float* out, cudaStream_t st) {
+  gaussian_update_fwd_kernel<<<dim3((HW + 255) / 256, B), 256, 0, st>>>(dout, gmm0, HW, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_update_bwd(const float* gout, const float* dout, const float* gmm0, int B, int HW, float* gin,
+                              cudaStream_t st) {
+  gaussian_update_bwd_kernel<<<dim3((HW + 255) / 256, B), 256, 0, st>>>(gout, dout, gmm0, HW, gin);
+  return cudaGetLastError();
+}
+
+}  // namespace magnet

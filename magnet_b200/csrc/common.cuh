@@ -1,0 +1,37 @@
+// Shared device helpers for the MaGNet matching kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/magnet_b200.h"
+
+namespace magnet {
+
+// Kernel-side view of magnet_cost_args; k values travel in the launch parameters
+// (constant bank, uniform loads) so that no __constant__ symbol / extra copy is needed.
+struct CostParams {
+  int B, V, D, H, W, HW;
+  float kappa;
+  float inv_v_exact;  // 1/V when V is a power of two (exact), else 0 -> use IEEE division
+  float vf;           // float(V)
+  const float* __restrict__ ref_feat;
+  const float* __restrict__ src_feat;
+  const float* __restrict__ src_gmm;
+  const float* __restrict__ rays;
+  const magnet_camera* __restrict__ cams;
+  const float* __restrict__ d_volume;
+  const float* __restrict__ ref_gmm;
+  float* __restrict__ out;
+  float k[MAGNET_MAX_PLANES];
+};
+
+// 1/x to <1 ulp: MUFU.RCP + one Newton step.  x == 0 -> NaN/inf, which the callers'
+// coordinate clamp turns into "out of bounds" (same outcome as the reference's +-10 clamp).
+__device__ __forceinline__ float rcp_nr(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return __fmaf_rn(r, __fmaf_rn(-x, r, 1.0f), r);
+}
+
+__device__ __forceinline__ float ldg_f(const float* p) { return __ldg(p); }
+
+}  // namespace magnet

@@ -1,0 +1,136 @@
+"""B200-native matching loop: the iteration of models/MAGNET.py:150-169 with the sampler fused into
+the cost kernel and the Gaussian update as one kernel, prepared once per forward.
+
+The reference inlines the sampler (MAGNET.py:154-156) and the update (inside GNET.forward, :60-69),
+so they are only reachable through this alternative loop (or the ``GNET`` mirror below); the
+cost-volume function itself is also available as a pure drop-in (``magnet_b200.homography``).
+The G-Net / mask-head convolutions stay ordinary ``nn.Module``s (cuDNN), as north_star states.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .sampling import depth_sampling
+
+
+class GNET(nn.Module):
+    """Mirror of the reference's ``GNET`` (models/MAGNET.py:47-70): same sub-module names and shapes
+    (``gnet.0 .. gnet.6``), hence state-dict compatible; the update equations run in the
+    ``magnet_gaussian_update`` kernels (forward + backward) instead of six elementwise ATen ops."""
+
+    def __init__(self, ch_in: int, ch_out: int = 2):
+        super().__init__()
+        h_dim = 128
+        self.gnet = nn.Sequential(
+            nn.Conv2d(ch_in, h_dim, 3, padding=1), nn.ReLU(inplace=True),
+            nn.Conv2d(h_dim, h_dim, 1), nn.ReLU(inplace=True),
+            nn.Conv2d(h_dim, h_dim, 1), nn.ReLU(inplace=True),
+            nn.Conv2d(h_dim, ch_out, 1),
+        )
+
+    def forward(self, cost_volume: torch.Tensor, ref_gmm: torch.Tensor) -> torch.Tensor:
+        return ops.gaussian_update(self.gnet(cost_volume), ref_gmm)
+
+
+class MatchingPlan:
+    """Everything about one batch that does not change across the N_iter iterations, prepared once:
+    device intrinsics / rays, camera-constant table, source features in the gather layout."""
+
+    def __init__(self, ref_feat, nghbr_feat, nghbr_gmms, nghbr_poses, is_valid, cam_intrins, *,
+                 thres: int = 5, src_layout: int = _lib.SRC_C4HW4):
+        dev = ref_feat.device
+        self.B, self.C, self.H, self.W = ref_feat.shape
+        self.V = nghbr_feat.shape[0] // self.B
+        self.kappa = float(thres)
+        self.ref_feat = ref_feat.detach().contiguous()
+        self.src_gmm = nghbr_gmms.detach().contiguous()
+        self.rays = cam_intrins['unit_ray_array_2D'].to(dev, torch.float32).contiguous()
+        intM = cam_intrins['intM'].to(dev, torch.float32).contiguous()
+        R, t = nghbr_poses[:, :, :3, :3], nghbr_poses[:, :, :3, 3]
+        self.cams = ops.pack_cameras(intM, R, t, is_valid.to(dev, torch.int32))
+        if src_layout == _lib.SRC_C4HW4 and self.C % 4 == 0:
+            self.src, self.layout = ops.repack_c4hw4(nghbr_feat.detach()), _lib.SRC_C4HW4
+        else:
+            self.src, self.layout = nghbr_feat.detach().contiguous(), _lib.SRC_NCHW
+
+    def cost(self, gmm: torch.Tensor, k, out: Optional[torch.Tensor] = None, variant=_lib.VARIANT_AUTO):
+        """Fused sampler + CW cost volume for the current Gaussian (B,2,H,W)."""
+        return ops.cost_volume(self.ref_feat, self.src, self.rays, self.cams, V=self.V, src_layout=self.layout,
+                               consistency=True, src_gmm=self.src_gmm, kappa=self.kappa, ref_gmm=gmm.detach(),
+                               k=k, out=out, variant=variant)
+
+
+def matching_loop(plan: MatchingPlan, ref_gmms: torch.Tensor, x_d3: torch.Tensor,
+                  g_net_convs: Callable[[torch.Tensor], torch.Tensor], n_iter: int, k: Sequence[float],
+                  variant=_lib.VARIANT_AUTO) -> List[torch.Tensor]:
+    """pred_list of MAGNET.py:150-169: [ref_gmms, pred_1, ..., pred_n_iter] at quarter resolution.
+
+    ``g_net_convs`` maps the (B, D+256, H, W) concatenation [cost volume, x_d3] to the raw (B,2,H,W)
+    G-Net output (``GNET.gnet``).  Gradients flow exactly where the reference lets them: through the
+    update into the conv weights, never into the cost volume (MAGNET.py:167 detaches it)."""
+    karr = ops.k_array(k)
+    preds = [ref_gmms]
+    for _ in range(n_iter):
+        cur = preds[-1].detach()
+        cv = plan.cost(cur, karr, variant=variant)
+        raw = g_net_convs(torch.cat([cv, x_d3], dim=1))
+        preds.append(ops.gaussian_update(raw, cur))
+    return preds
+
+
+class MagnetHead(nn.Module):
+    """G-Net + mask head + convex upsampling of the reference's ``MAGNET`` (models/MAGNET.py:100-118,
+    150-175) operating on backbone outputs; D-Net / F-Net are supplied by the caller (they need
+    checkpoints / torch.hub in the reference and are out of scope)."""
+
+    def __init__(self, n_samples: int = 5, sampling_range: float = 3, n_iter: int = 3, thres: int = 5,
+                 downsample_ratio: int = 4, dnet_fdim: int = 256):
+        super().__init__()
+        self.n_iter, self.thres, self.downsample_ratio = n_iter, thres, downsample_ratio
+        self.k_list = depth_sampling(sampling_range, n_samples)
+        self.g_net = GNET(ch_in=dnet_fdim + n_samples, ch_out=2)
+        h_dim = 128
+        self.mask_head = nn.Sequential(
+            nn.Conv2d(dnet_fdim, h_dim, 3, padding=1), nn.ReLU(inplace=True),
+            nn.Conv2d(h_dim, h_dim, 1), nn.ReLU(inplace=True),
+            nn.Conv2d(h_dim, h_dim, 1), nn.ReLU(inplace=True),
+            nn.Conv2d(h_dim, 9 * downsample_ratio * downsample_ratio, 1),
+        )
+
+    @staticmethod
+    def upsample(depth, up_mask, k):
+        N, o_dim, H, W = depth.shape
+        m = torch.softmax(up_mask.view(N, 1, 9, k, k, H, W), dim=2)
+        nb = nn.functional.unfold(depth, [3, 3], padding=1).view(N, o_dim, 9, 1, 1, H, W)
+        return torch.sum(m * nb, dim=2).permute(0, 1, 4, 2, 5, 3).reshape(N, o_dim, k * H, k * W)
+
+    def forward(self, ref_feat, nghbr_feat, ref_gmms, nghbr_gmms, x_d3, nghbr_poses, is_valid, cam_intrins):
+        plan = MatchingPlan(ref_feat, nghbr_feat, nghbr_gmms, nghbr_poses, is_valid, cam_intrins, thres=self.thres)
+        preds = matching_loop(plan, ref_gmms, x_d3, self.g_net.gnet, self.n_iter, self.k_list)
+        mask = self.mask_head(x_d3)
+        return [self.upsample(pr, mask, self.downsample_ratio) for pr in preds[1:]]
+
+
+def install(homography_module=None) -> None:
+    """Rebind the reference's operators to the B200 kernels so that ``MAGNET.forward`` /
+    ``MAGNET_F.forward`` / ``test_MaGNet.py`` run unchanged:
+
+        import models.submodules.homography as homography   # the reference's module
+        import magnet_b200; magnet_b200.install(homography)
+
+    With no argument the module is looked up in ``sys.modules`` under its reference name."""
+    import sys
+
+    from . import homography as ours
+
+    ours_lib = _lib.lib()   # fail now, loudly, if the CUDA library is missing
+    del ours_lib
+    mod = homography_module or sys.modules.get("models.submodules.homography")
+    if mod is None:
+        raise _lib.MagnetError("models.submodules.homography is not imported; pass the module to install()")
+    mod.est_costvolume_CW = ours.est_costvolume_CW
+    mod.est_costvolume_F = ours.est_costvolume_F

@@ -1,0 +1,174 @@
+"""Tensor-level wrappers over the C ABI (one Python call = one kernel launch) and the
+``torch.autograd.Function`` wrappers the reference-facing modules use.
+
+Everything here requires CUDA tensors and the built library; nothing falls back to PyTorch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import CostArgs, check, lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda_f32(name: str, x: torch.Tensor, contiguous: bool = True) -> torch.Tensor:
+    if not isinstance(x, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not x.is_cuda:
+        raise _lib.MagnetError(f"{name} must be a CUDA tensor (magnet_b200 has no CPU path)")
+    if x.dtype != torch.float32:
+        raise _lib.MagnetError(f"{name} must be float32 (the reference path is fp32-only, homography.py:130)")
+    if contiguous and not x.is_contiguous():
+        x = x.contiguous()
+    return x
+
+
+def k_array(k: Sequence[float]):
+    """Python / numpy / tensor sequence -> host float[D] (rounded to fp32 like torch does for
+    tensor * python-scalar, MAGNET.py:155)."""
+    if isinstance(k, torch.Tensor):
+        k = k.detach().cpu().flatten().tolist()
+    vals = [float(v) for v in k]
+    if len(vals) > _lib.MAGNET_MAX_PLANES:
+        raise _lib.MagnetError(f"at most {_lib.MAGNET_MAX_PLANES} hypotheses per call, got {len(vals)}")
+    return (C.c_float * len(vals))(*vals)
+
+
+def pack_cameras(intM: torch.Tensor, R: torch.Tensor, t: torch.Tensor, is_valid: torch.Tensor) -> torch.Tensor:
+    """(B,3,3) intrinsics, (B,V,3,3) / (B,V,3) pose views (any strides), (B,V) int32 validity — all on the
+    device — -> (B*V, 16) float32 camera-constant table (struct magnet_camera)."""
+    intM = _need_cuda_f32("intM", intM)
+    R = _need_cuda_f32("R", R, contiguous=False)
+    t = _need_cuda_f32("t", t, contiguous=False)
+    B, V = R.shape[0], R.shape[1]
+    if is_valid.dtype != torch.int32 or not is_valid.is_cuda:
+        is_valid = is_valid.to(device=intM.device, dtype=torch.int32)
+    is_valid = is_valid.contiguous()
+    cams = torch.empty(B * V, 16, device=intM.device, dtype=torch.float32)
+    rs, ts = R.stride(), t.stride()
+    check(lib().magnet_pack_cameras_f32(intM.data_ptr(), R.data_ptr(), rs[0], rs[1], rs[2], rs[3],
+                                        t.data_ptr(), ts[0], ts[1], ts[2], is_valid.data_ptr(), B, V,
+                                        cams.data_ptr(), _stream()), "magnet_pack_cameras_f32")
+    return cams
+
+
+def repack_c4hw4(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(N,C,H,W) -> (N,C/4,H,W,4) source-feature layout consumed by the tap-sharing kernel."""
+    x = _need_cuda_f32("x", x)
+    N, Cc, H, W = x.shape
+    if out is None:
+        out = torch.empty(N, Cc // 4, H, W, 4, device=x.device, dtype=torch.float32)
+    check(lib().magnet_repack_c4hw4_f32(x.data_ptr(), out.data_ptr(), N, Cc, H, W, _stream()),
+          "magnet_repack_c4hw4_f32")
+    return out
+
+
+def sample_depths(gmm: torch.Tensor, k, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Sampler alone (MAGNET.py:154-156): gmm (B,2,H,W) -> d_volume (B,D,H,W)."""
+    gmm = _need_cuda_f32("gmm", gmm)
+    karr = k if isinstance(k, C.Array) else k_array(k)
+    B, _, H, W = gmm.shape
+    D = len(karr)
+    if out is None:
+        out = torch.empty(B, D, H, W, device=gmm.device, dtype=torch.float32)
+    check(lib().magnet_sample_depths_f32(gmm.data_ptr(), C.cast(karr, C.c_void_p), B, D, H * W, out.data_ptr(),
+                                         _stream()), "magnet_sample_depths_f32")
+    return out
+
+
+def cost_volume(ref_feat: torch.Tensor, src_feat: torch.Tensor, rays: torch.Tensor, cams: torch.Tensor, *,
+                V: int, src_layout: int, consistency: bool, src_gmm: Optional[torch.Tensor] = None,
+                kappa: float = 5.0, d_volume: Optional[torch.Tensor] = None,
+                ref_gmm: Optional[torch.Tensor] = None, k=None, planes: bool = False, softmax: bool = False,
+                variant: int = _lib.VARIANT_AUTO, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One launch of magnet_cost_volume_f32.  Depth source: ``d_volume`` (drop-in), or ``ref_gmm`` + ``k``
+    (fused sampler), or ``k`` with ``planes=True`` (fronto-parallel planes)."""
+    ref_feat = _need_cuda_f32("ref_feat", ref_feat)
+    src_feat = _need_cuda_f32("src_feat", src_feat)
+    rays = _need_cuda_f32("rays", rays)
+    cams = _need_cuda_f32("cams", cams)
+    B, Cc, H, W = ref_feat.shape
+    a = CostArgs()
+    a.B, a.V, a.C, a.H, a.W = B, V, Cc, H, W
+    a.src_layout = src_layout
+    a.consistency = 1 if consistency else 0
+    a.softmax = 1 if softmax else 0
+    a.variant = variant
+    a.kappa = float(kappa)
+    a.ref_feat, a.src_feat, a.rays, a.cams = ref_feat.data_ptr(), src_feat.data_ptr(), rays.data_ptr(), cams.data_ptr()
+    keep = [ref_feat, src_feat, rays, cams]
+    if consistency:
+        src_gmm = _need_cuda_f32("src_gmm", src_gmm)
+        a.src_gmm = src_gmm.data_ptr()
+        keep.append(src_gmm)
+    karr = None
+    if d_volume is not None:
+        d_volume = _need_cuda_f32("d_volume", d_volume)
+        a.depth_mode, a.D, a.d_volume = _lib.DEPTH_VOLUME, d_volume.shape[1], d_volume.data_ptr()
+        keep.append(d_volume)
+    else:
+        karr = k if isinstance(k, C.Array) else k_array(k)
+        a.D = len(karr)
+        a.k_host = C.cast(karr, C.c_void_p)
+        if planes:
+            a.depth_mode = _lib.DEPTH_PLANES
+        else:
+            ref_gmm = _need_cuda_f32("ref_gmm", ref_gmm)
+            a.depth_mode, a.ref_gmm = _lib.DEPTH_GAUSS, ref_gmm.data_ptr()
+            keep.append(ref_gmm)
+    if out is None:
+        out = torch.empty(B, a.D, H, W, device=ref_feat.device, dtype=torch.float32)
+    a.out = out.data_ptr()
+    check(lib().magnet_cost_volume_f32(C.byref(a), _stream()), "magnet_cost_volume_f32")
+    return out
+
+
+def cost_launch_info(B, V, D, Cc, H, W, variant=_lib.VARIANT_AUTO):
+    """(grid CTAs, threads per CTA, dynamic smem bytes) the cost kernel would use for these sizes."""
+    a = CostArgs()
+    a.B, a.V, a.D, a.C, a.H, a.W = B, V, D, Cc, H, W
+    a.depth_mode, a.src_layout, a.consistency, a.variant = _lib.DEPTH_PLANES, _lib.SRC_NCHW, 0, variant
+    dummy = (C.c_float * 1)(0.0)
+    one = C.cast(dummy, C.c_void_p)
+    a.ref_feat = a.src_feat = a.rays = a.cams = a.out = a.k_host = one   # validated for non-NULL only
+    g, b, s = C.c_int(), C.c_int(), C.c_int()
+    check(lib().magnet_cost_launch_info(C.byref(a), C.byref(g), C.byref(b), C.byref(s)), "magnet_cost_launch_info")
+    return g.value, b.value, s.value
+
+
+class GaussianUpdate(torch.autograd.Function):
+    """mu' = mu0 + mu1*sigma0 ; sigma' = (elu(sigma1) + 1 + 1e-10)*sigma0  (MAGNET.py:60,65-69).
+    Differentiable w.r.t. the G-Net output only; ``ref_gmm`` is detached in the reference (MAGNET.py:168)."""
+
+    @staticmethod
+    def forward(ctx, d_output: torch.Tensor, ref_gmm: torch.Tensor) -> torch.Tensor:
+        d_output = _need_cuda_f32("d_output", d_output)
+        ref_gmm = _need_cuda_f32("ref_gmm", ref_gmm.detach())
+        B, _, H, W = d_output.shape
+        out = torch.empty_like(d_output)
+        check(lib().magnet_gaussian_update_fwd_f32(d_output.data_ptr(), ref_gmm.data_ptr(), B, H * W,
+                                                   out.data_ptr(), _stream()), "magnet_gaussian_update_fwd_f32")
+        ctx.save_for_backward(d_output, ref_gmm)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: torch.Tensor):
+        d_output, ref_gmm = ctx.saved_tensors
+        grad_out = _need_cuda_f32("grad_out", grad_out)
+        B, _, H, W = d_output.shape
+        gin = torch.empty_like(d_output)
+        check(lib().magnet_gaussian_update_bwd_f32(grad_out.data_ptr(), d_output.data_ptr(), ref_gmm.data_ptr(),
+                                                   B, H * W, gin.data_ptr(), _stream()),
+              "magnet_gaussian_update_bwd_f32")
+        return gin, None
+
+
+def gaussian_update(d_output: torch.Tensor, ref_gmm: torch.Tensor) -> torch.Tensor:
+    return GaussianUpdate.apply(d_output, ref_gmm)

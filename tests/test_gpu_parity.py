@@ -1,0 +1,211 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle, the reference-generated golden
+vectors, the analytic known answers, and size-independent properties at BASELINE.json's full sizes.
+
+Bar: |got - want| <= 1e-4 * max|want| on every element whose consistency mask agrees;
+elements on the hard threshold may flip and are counted against a budget (tests/util.py)."""
+import numpy as np
+import pytest
+import torch
+
+import magnet_b200
+from magnet_b200 import _lib, ops
+from magnet_b200.synthetic import make_config, make_inputs
+from oracle import magnet_oracle as mo
+from tests import kat
+from tests.util import compare_volume, golden_inputs, load_golden, oracle_cw
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = [("direct", _lib.VARIANT_DIRECT), ("cells", _lib.VARIANT_CELLS)]
+
+
+def _run_cw(inp, dvol, dev, variant):
+    g = inp.to(dev)
+    out = magnet_b200.est_costvolume_CW(dvol.to(dev), g.ref_feat, g.nghbr_feat, g.ref_gmms, g.nghbr_gmms, g.R, g.t,
+                                        inp.is_valid, inp.cam_intrins, inp.thres, variant=variant)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("vname,variant", VARIANTS)
+@pytest.mark.parametrize("name", ["cw_small_random", "cw_small_smooth", "cw_c64_d64", "cw_kitti", "cw_cfg1"])
+def test_cw_matches_reference_golden(cuda, name, vname, variant):
+    """The reference's own outputs (frozen in tests/golden) are the pin; the oracle supplies flip margins."""
+    z, inp = golden_inputs(name)
+    dvol = torch.from_numpy(mo.depth_sampler(inp.ref_gmms[:, 0].numpy(), inp.ref_gmms[:, 1].numpy(), z["k_list"]))
+    got = _run_cw(inp, dvol, cuda, variant)
+    _, margin = oracle_cw(inp, dvol.numpy(), return_margin=True)
+    rep = compare_volume(got, z["cost_cw"], margin, what=f"{name}/{vname}")
+    print(name, vname, rep)
+
+
+@pytest.mark.parametrize("vname,variant", VARIANTS)
+@pytest.mark.parametrize("case", sorted(kat.CW_CASES))
+def test_cw_known_answers_gpu(cuda, case, vname, variant):
+    inp, dvol, exp, tol = kat.CW_CASES[case]()
+    got = _run_cw(inp, dvol, cuda, variant)
+    if tol == 0.0:
+        assert np.array_equal(got, exp.astype(np.float32))
+    else:
+        assert np.abs(got - exp).max() <= tol * max(np.abs(exp).max(), 1.0)
+    if case == "one_pixel_shift":
+        assert np.array_equal(got[..., -1], np.zeros_like(got[..., -1]))
+
+
+@pytest.mark.parametrize("seed,depth,shape", [
+    (21, "random", dict(B=2, V=2, D=5, H=17, W=23, C=16)),       # ragged: HW not a multiple of 32/128
+    (22, "smooth", dict(B=1, V=4, D=64, H=30, W=40, C=64)),
+    (23, "random", dict(B=1, V=1, D=33, H=9, W=50, C=32)),       # > NCELL cells per lane -> several rounds
+    (24, "smooth", dict(B=3, V=3, D=16, H=12, W=12, C=20)),      # C not instantiated by the cells kernel -> direct
+])
+def test_cw_vs_oracle_seeded(cuda, seed, depth, shape):
+    inp = make_inputs(seed=seed, depth=depth, invalid=[(0, 0)] if shape["V"] > 1 else (), **shape)
+    dvol = inp.depth_volume()
+    want, margin = oracle_cw(inp, dvol.numpy(), return_margin=True)
+    for vname, variant in VARIANTS:
+        if variant == _lib.VARIANT_CELLS and shape["C"] not in (16, 32, 64):
+            with pytest.raises(_lib.MagnetError):
+                _run_cw(inp, dvol, cuda, variant)
+            continue
+        got = _run_cw(inp, dvol, cuda, variant)
+        compare_volume(got, want, margin, what=f"seed{seed}/{vname}")
+    got = _run_cw(inp, dvol, cuda, _lib.VARIANT_AUTO)
+    compare_volume(got, want, margin, what=f"seed{seed}/auto")
+
+
+def test_fused_sampler_equals_drop_in(cuda):
+    """MAGNET_DEPTH_GAUSS (sampler fused) must reproduce MAGNET_DEPTH_VOLUME bit for bit: d_j is formed
+    with the same separately rounded multiply and add (MAGNET.py:155)."""
+    inp = make_inputs(B=2, V=3, D=16, H=24, W=32, C=64, seed=31, depth="smooth")
+    g = inp.to(cuda)
+    plan = magnet_b200.MatchingPlan(g.ref_feat, g.nghbr_feat, g.nghbr_gmms, g.nghbr_poses, inp.is_valid,
+                                    inp.cam_intrins, thres=inp.thres)
+    fused = plan.cost(g.ref_gmms, inp.k.tolist())
+    dvol = ops.sample_depths(g.ref_gmms, inp.k.tolist())
+    assert torch.equal(dvol.cpu(), inp.depth_volume())
+    drop = magnet_b200.est_costvolume_CW(dvol, g.ref_feat, g.nghbr_feat, g.ref_gmms, g.nghbr_gmms, g.R, g.t,
+                                         inp.is_valid, inp.cam_intrins, inp.thres)
+    assert torch.equal(fused, drop)
+    nchw = ops.cost_volume(g.ref_feat, g.nghbr_feat, plan.rays, plan.cams, V=inp.V, src_layout=_lib.SRC_NCHW,
+                           consistency=True, src_gmm=g.nghbr_gmms, kappa=5.0, ref_gmm=g.ref_gmms, k=inp.k.tolist(),
+                           variant=_lib.VARIANT_CELLS)
+    assert torch.equal(fused, nchw), "C4HW4 and NCHW gathers must agree exactly"
+
+
+@pytest.mark.parametrize("vname,variant", VARIANTS)
+@pytest.mark.parametrize("name", ["cw_small_random", "cw_c64_d64", "cw_kitti"])
+def test_f_volume_matches_reference_golden(cuda, name, vname, variant):
+    z, inp = golden_inputs(name)
+    g = inp.to(cuda)
+    dc = torch.from_numpy(z["planes"]).view(1, -1, 1, 1).to(cuda)
+    got = magnet_b200.est_costvolume_F(dc, g.ref_feat, g.nghbr_feat, g.R, g.t, inp.is_valid, inp.cam_intrins,
+                                       variant=variant).cpu().numpy()
+    want = z["cost_f"]
+    assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max(), np.abs(got - want).max()
+    assert np.allclose(got.sum(axis=1), 1.0, atol=1e-5)
+
+
+def test_f_identity_uniform_gpu(cuda):
+    inp, planes, exp, _ = kat.f_identity()
+    g = inp.to(cuda)
+    got = magnet_b200.est_costvolume_F(torch.from_numpy(planes).view(1, -1, 1, 1), g.ref_feat, g.nghbr_feat, g.R, g.t,
+                                       inp.is_valid, inp.cam_intrins).cpu().numpy()
+    assert np.abs(got - exp).max() <= 1e-6
+
+
+def test_update_sampler_kernels_vs_golden(cuda):
+    z, _ = load_golden("update_upsample")
+    d_out = torch.from_numpy(z["d_output"]).to(cuda).requires_grad_(True)
+    ref_gmm = torch.from_numpy(z["ref_gmm"]).to(cuda)
+    new = ops.gaussian_update(d_out, ref_gmm)
+    (new * torch.from_numpy(z["grad_out"]).to(cuda)).sum().backward()
+    assert np.allclose(new.detach().cpu().numpy(), z["new_gmm"], rtol=2e-6, atol=1e-6)
+    assert np.allclose(d_out.grad.cpu().numpy(), z["grad_d_output"], rtol=2e-6, atol=1e-6)
+    # the GNET mirror is state-dict compatible with the reference's module names and uses the same kernels
+    gn = magnet_b200.GNET(ch_in=6).to(cuda)
+    assert sorted(gn.state_dict()) == sorted(f"gnet.{i}.{p}" for i in (0, 2, 4, 6) for p in ("weight", "bias"))
+    x = torch.randn(2, 6, 9, 11, device=cuda)
+    out = gn(x, ref_gmm)
+    raw = gn.gnet(x)
+    want = mo.gaussian_update(raw.detach().cpu().numpy(), z["ref_gmm"])
+    assert np.allclose(out.detach().cpu().numpy(), want, rtol=2e-6, atol=1e-6)
+    out.sum().backward()
+    assert gn.gnet[6].weight.grad is not None and torch.isfinite(gn.gnet[6].weight.grad).all()
+
+
+def test_install_rebinds_reference_module(cuda):
+    """install() makes a module shaped like models.submodules.homography call the kernels, and the
+    reference's loop (restated in oracle/torch_ref.matching_iterations) then runs on them unchanged."""
+    import types
+    from oracle import torch_ref
+    fake = types.ModuleType("models.submodules.homography")
+    fake.est_costvolume_CW = torch_ref.cost_volume_cw
+    fake.est_costvolume_F = torch_ref.cost_volume_f
+    magnet_b200.install(fake)
+    assert fake.est_costvolume_CW is magnet_b200.est_costvolume_CW
+    inp = make_inputs(B=2, V=2, D=5, H=16, W=24, C=16, seed=41, depth="smooth")
+    g = inp.to(cuda)
+    torch.manual_seed(0)
+    head = magnet_b200.GNET(ch_in=5 + 8).to(cuda)
+    x_d3 = torch.randn(2, 8, 16, 24, device=cuda)
+    klist = magnet_b200.depth_sampling(3, 5)
+    # loop on the B200 kernels (sampler fused, update kernel) ...
+    plan = magnet_b200.MatchingPlan(g.ref_feat, g.nghbr_feat, g.nghbr_gmms, g.nghbr_poses, inp.is_valid,
+                                    inp.cam_intrins, thres=5)
+    ours = magnet_b200.matching_loop(plan, g.ref_gmms, x_d3, head.gnet, 3, klist)
+    # ... against the ATen port of the reference loop on the same device (reference-CUDA path)
+    theirs = torch_ref.matching_iterations(g, head.gnet, x_d3, 3, klist, 5)
+    for a, b in zip(ours[1:], theirs[1:]):
+        d = (a - b).abs()
+        # a flipped mask element changes one G-Net input; allow a tiny fraction of visibly different pixels
+        assert float((d > 1e-3 * b.abs().max()).float().mean()) < 2e-3
+        assert float(d.median()) < 1e-5
+
+
+def test_full_size_properties_cfg2(cuda):
+    """BASELINE configs[1] (B=8,V=4,D=64,120x160,C=64): too big for the oracle, so check properties:
+    direct and tap-sharing kernels agree; scaling ref features by 2 scales the volume by exactly 2;
+    an all-invalid batch element is exactly zero; view order does not matter beyond fp32 summation order."""
+    inp = make_config("cfg2", seed=1, invalid=[(3, 0), (3, 1), (3, 2), (3, 3)])
+    g = inp.to(cuda)
+    plan = magnet_b200.MatchingPlan(g.ref_feat, g.nghbr_feat, g.nghbr_gmms, g.nghbr_poses, inp.is_valid,
+                                    inp.cam_intrins, thres=5)
+    k = inp.k.tolist()
+    cells = plan.cost(g.ref_gmms, k, variant=_lib.VARIANT_CELLS)
+    direct = plan.cost(g.ref_gmms, k, variant=_lib.VARIANT_DIRECT)
+    assert torch.isfinite(cells).all()
+    assert float(cells[3].abs().max()) == 0.0
+    scale = float(direct.abs().max())
+    d = (cells - direct).abs()
+    frac_bad = float((d > 1e-4 * scale).float().mean())
+    print("cfg2 cells-vs-direct: max rel", float(d.max()) / scale, "frac beyond 1e-4", frac_bad,
+          "nonzero frac", float((cells != 0).float().mean()))
+    assert frac_bad <= 3e-5
+    plan2 = magnet_b200.MatchingPlan(g.ref_feat * 2.0, g.nghbr_feat, g.nghbr_gmms, g.nghbr_poses, inp.is_valid,
+                                     inp.cam_intrins, thres=5)
+    assert torch.equal(plan2.cost(g.ref_gmms, k, variant=_lib.VARIANT_CELLS), cells * 2.0)
+    # reverse the view order (features, Gaussians, poses, validity all permuted consistently)
+    B, V = inp.B, inp.V
+    perm = torch.arange(V - 1, -1, -1)
+    idx = (perm[:, None] * B + torch.arange(B)[None]).reshape(-1).to(cuda)
+    plan3 = magnet_b200.MatchingPlan(g.ref_feat, g.nghbr_feat[idx], g.nghbr_gmms[idx], g.nghbr_poses[:, perm.to(cuda)],
+                                     inp.is_valid[:, perm], inp.cam_intrins, thres=5)
+    rev = plan3.cost(g.ref_gmms, k, variant=_lib.VARIANT_CELLS)
+    assert float((rev - cells).abs().max()) <= 2e-6 * scale
+
+
+def test_full_size_identity_known_answer_cfg3(cuda):
+    """KITTI-shape grid (B=4,V=4,D=64,88x304): identity pose + open mask => per-pixel dot, every plane."""
+    inp = make_config("cfg3", seed=2)
+    inp.nghbr_poses.zero_()
+    for i in range(4):
+        inp.nghbr_poses[:, :, i, i] = 1.0
+    inp.nghbr_gmms[:, 1] = 1e6
+    g = inp.to(cuda)
+    plan = magnet_b200.MatchingPlan(g.ref_feat, g.nghbr_feat, g.nghbr_gmms, g.nghbr_poses, inp.is_valid,
+                                    inp.cam_intrins, thres=5)
+    got = plan.cost(g.ref_gmms, inp.k.tolist())
+    B, V = inp.B, inp.V
+    dots = torch.stack([(g.ref_feat * g.nghbr_feat[v * B:(v + 1) * B]).sum(1) for v in range(V)]).mean(0)
+    err = (got - dots[:, None]).abs().max()
+    assert float(err) <= 1e-4 * float(dots.abs().max())

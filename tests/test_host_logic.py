@@ -1,0 +1,132 @@
+"""CPU-side tests: C-ABI exports and argument validation (no compute calls), sampler offsets, prep cache,
+shard arithmetic."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from magnet_b200 import _lib
+from magnet_b200._lib import CostArgs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    L = _lib.lib()
+    header = open(os.path.join(ROOT, "include", "magnet_b200.h")).read()
+    declared = set(re.findall(r"\b(magnet_[a-z0-9_]+)\s*\(", header))
+    declared -= {"magnet_status", "magnet_camera", "magnet_cost_args"}
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.magnet_abi_version() == _lib.MAGNET_ABI_VERSION
+    assert L.magnet_strerror(0) == b"ok"
+    assert C.sizeof(CostArgs) == 12 * 4 + 9 * 8
+
+
+def test_cost_args_validation_without_gpu():
+    L = _lib.lib()
+    assert L.magnet_cost_volume_f32(None, None) == _lib.ERR_NULL
+    a = CostArgs()
+    assert L.magnet_cost_volume_f32(C.byref(a), None) == _lib.ERR_SHAPE
+    a.B, a.V, a.D, a.C, a.H, a.W = 1, 2, 4, 16, 8, 8
+    assert L.magnet_cost_volume_f32(C.byref(a), None) == _lib.ERR_NULL          # pointers missing
+    buf = (C.c_float * 64)()
+    p = C.cast(buf, C.c_void_p)
+    a.ref_feat = a.src_feat = a.rays = a.cams = a.out = p
+    a.depth_mode = _lib.DEPTH_VOLUME
+    assert L.magnet_cost_volume_f32(C.byref(a), None) == _lib.ERR_NULL          # d_volume missing
+    a.depth_mode = 7
+    assert L.magnet_cost_volume_f32(C.byref(a), None) == _lib.ERR_UNSUPPORTED
+    a.depth_mode = _lib.DEPTH_PLANES
+    a.k_host = p
+    a.D = _lib.MAGNET_MAX_PLANES + 1
+    assert L.magnet_cost_volume_f32(C.byref(a), None) == _lib.ERR_UNSUPPORTED
+    a.D = 4
+    a.consistency = 1                                                           # needs src_gmm
+    assert L.magnet_cost_volume_f32(C.byref(a), None) == _lib.ERR_NULL
+    a.consistency = 0
+    a.src_layout = _lib.SRC_C4HW4
+    a.C = 18
+    assert L.magnet_cost_volume_f32(C.byref(a), None) == _lib.ERR_UNSUPPORTED   # C % 4
+    a.C = 16
+    a.src_feat = C.c_void_p(C.addressof(buf) + 4)
+    assert L.magnet_cost_volume_f32(C.byref(a), None) == _lib.ERR_ALIGN
+    a.src_feat = p
+    a.variant = _lib.VARIANT_CELLS
+    a.C = 20
+    assert L.magnet_cost_volume_f32(C.byref(a), None) == _lib.ERR_UNSUPPORTED   # cells kernel: C in {16,32,64}
+    assert L.magnet_repack_c4hw4_f32(p, p, 1, 6, 2, 2, None) == _lib.ERR_UNSUPPORTED
+    assert L.magnet_gaussian_update_fwd_f32(None, p, 1, 4, p, None) == _lib.ERR_NULL
+    with pytest.raises(_lib.MagnetError):
+        _lib.check(_lib.ERR_SHAPE, "x")
+
+
+def test_launch_info_matches_design():
+    from magnet_b200 import ops
+    grid, block, smem = ops.cost_launch_info(8, 4, 64, 64, 120, 160)
+    assert (grid, block) == (8 * 150, 128)
+    assert smem == 8 * 3 * 128 * 16 + 8 * 128 * 8 + 64 * 128 * 4
+    grid, block, smem = ops.cost_launch_info(8, 4, 64, 64, 120, 160, variant=_lib.VARIANT_DIRECT)
+    assert (grid, block, smem) == (150 * 64 * 8, 128, 0)
+
+
+def test_ops_refuse_cpu_tensors():
+    from magnet_b200 import ops
+    x = torch.zeros(1, 2, 4, 4)
+    with pytest.raises(_lib.MagnetError):
+        ops.gaussian_update(x, x)
+    with pytest.raises(_lib.MagnetError):
+        ops.repack_c4hw4(torch.zeros(1, 4, 2, 2))
+
+
+def test_k_offsets():
+    from magnet_b200.sampling import depth_sampling, k_offsets_f32
+    k64 = depth_sampling(3, 64)
+    assert len(k64) == 64 and abs(k64[0] + 2.560835) < 1e-5 and abs(k64[-1] - 2.560835) < 1e-5
+    assert np.allclose(k64, -np.asarray(k64)[::-1], atol=1e-12)
+    gaps = np.diff(k64)
+    assert 0.03 < gaps.min() < 0.05 and 0.5 < gaps.max() < 0.6
+    assert k_offsets_f32(3, 5).dtype == np.float32
+
+
+def test_prep_cache_identity_and_version():
+    from magnet_b200.homography import _PrepCache
+    c = _PrepCache(capacity=2)
+    a = torch.zeros(3)
+    assert c.get("x", (a,)) is None
+    c.put("x", (a,), "va")
+    assert c.get("x", (a,)) == "va"
+    a.add_(1)                                  # in-place modification bumps _version -> miss
+    assert c.get("x", (a,)) is None
+    b = torch.zeros(3)
+    c.put("x", (b,), "vb")
+    del b                                      # dead tensor can never hit, even if id() is reused
+    d = torch.zeros(3)
+    assert c.get("x", (d,)) is None
+
+
+def test_shard_range_partitions_exactly():
+    from magnet_b200.dist import shard_range
+    for total in (1, 7, 8, 32, 33):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_synthetic_conventions():
+    from magnet_b200.synthetic import make_inputs, quarter_res_camera
+    K, rays = quarter_res_camera(120, 160)
+    assert np.allclose(K[0, 0], 144.4) and rays.shape == (3, 19200)
+    # ray of pixel (y=0, x=0) is the back-projected pixel CENTRE (dataloader_scannet.py:119-120,141-144)
+    assert np.allclose(rays[:, 0], [(0.5 - 80.0) / 144.4, (0.5 - 60.0) / 145.0, 1.0], atol=1e-6)
+    inp = make_inputs(B=2, V=3, D=5, H=8, W=8, C=4, seed=0, invalid=[(1, 0)])
+    assert inp.nghbr_feat.shape[0] == 6 and inp.is_valid.dtype == torch.int32 and not inp.is_valid.is_cuda
+    assert int(inp.is_valid[1, 0]) == 0 and inp.R.shape == (2, 3, 3, 3) and not inp.R.is_contiguous()
+    assert inp.depth_volume().shape == (2, 5, 8, 8)

@@ -2,7 +2,7 @@
 """bench.py — frames/s of MaGNet's multi-view matching hot path on B200 (BASELINE.json metric).
 
 One *step* = one pass of the hot path over one batch of synthetic frames per GPU:
-    source repack (NCHW -> C4HW4) + camera table  [once per batch, inside the timed region]
+    source repack (NCHW -> TILED32) + camera table  [once per batch, inside the timed region]
     N_iter = 3 x ( fused sampler + warp + bilinear sample + consistency + view fusion kernel
                    -> Gaussian update kernel on a fixed synthetic G-Net output )
 A *frame* is one reference image's full matching loop (SURVEY §8 d).  Workload at N=1 is BASELINE.json
@@ -198,7 +198,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--variant", default="auto", choices=["auto", "direct", "cells"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "direct", "cells", "cells_noreuse"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gnet", action="store_true")
     args = ap.parse_args()
@@ -219,7 +219,8 @@ def main():
     import magnet_b200
     from magnet_b200 import _lib, ops
     from magnet_b200.synthetic import make_config
-    variant = {"auto": _lib.VARIANT_AUTO, "direct": _lib.VARIANT_DIRECT, "cells": _lib.VARIANT_CELLS}[args.variant]
+    variant = {"auto": _lib.VARIANT_AUTO, "direct": _lib.VARIANT_DIRECT, "cells": _lib.VARIANT_CELLS,
+               "cells_noreuse": _lib.VARIANT_CELLS_NOREUSE}[args.variant]
 
     inp = make_config(args.config, seed=1 + rank)
     B, V, D = inp.B, inp.V, inp.D
@@ -233,20 +234,20 @@ def main():
     is_valid_d = inp.is_valid.to(dev)
     intM_d = inp.cam_intrins['intM'].to(dev)
     rays_d = inp.cam_intrins['unit_ray_array_2D'].to(dev).contiguous()
-    src_packed = torch.empty(V * B, C // 4, H, Wd, 4, device=dev)
+    src_packed = torch.empty(V * B, H, (Wd + 31) // 32, C // 4, 32, 4, device=dev)
     cv = torch.empty(B, D, H, Wd, device=dev)
     ev_pairs = []
 
     def hot_step(record=False):
         """repack + camera table + N_ITER x (fused cost kernel -> update kernel); everything device-resident."""
-        ops.repack_c4hw4(g.nghbr_feat, out=src_packed)
+        ops.repack_tiled32(g.nghbr_feat, out=src_packed)
         cams = ops.pack_cameras(intM_d, g.R, g.t, is_valid_d)
         pred = g.ref_gmms
         for _ in range(N_ITER):
             if record:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            ops.cost_volume(g.ref_feat, src_packed, rays_d, cams, V=V, src_layout=_lib.SRC_C4HW4, consistency=True,
+            ops.cost_volume(g.ref_feat, src_packed, rays_d, cams, V=V, src_layout=_lib.SRC_TILED32, consistency=True,
                             src_gmm=g.nghbr_gmms, kappa=float(inp.thres), ref_gmm=pred, k=karr, out=cv, variant=variant)
             if record:
                 e1.record()
@@ -345,7 +346,7 @@ def main():
     achieved = abytes / (kern_ms * 1e-3) / 1e9
     grid, block, smem = ops.cost_launch_info(B, V, D, C, H, Wd, variant=variant)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(args.config), "kernel": "cost_cells_kernel<64,GAUSS,C4HW4,CW>" if variant != _lib.VARIANT_DIRECT else "cost_direct_kernel<CW>",
+                "traffic": ncu_traffic(args.config), "kernel": "cost_cells_kernel<64,GAUSS,CW> (TILED32 gather)" if variant != _lib.VARIANT_DIRECT else "cost_direct_kernel<CW>",
                 "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src,
                 "launch": {"grid": grid, "block": block, "smem_bytes": smem}}
     cpu_baseline = None

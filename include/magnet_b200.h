@@ -46,8 +46,10 @@ typedef enum magnet_depth_mode {
 
 /* Memory layout of the source-view feature maps. */
 typedef enum magnet_src_layout {
-  MAGNET_SRC_NCHW = 0,  /* (V*B, C, H, W), the reference layout                                */
-  MAGNET_SRC_C4HW4 = 1  /* (V*B, C/4, H, W, 4): channel quads innermost, see magnet_repack_c4hw4_f32 */
+  MAGNET_SRC_NCHW = 0,   /* (V*B, C, H, W), the reference layout                               */
+  MAGNET_SRC_TILED32 = 1 /* (V*B, H, ceil(W/32), C/4, 32, 4): per row, tiles of 32 pixels; inside a tile
+                            the C/4 channel quads are 512 B apart and the 32 pixels of one quad are
+                            contiguous (see magnet_repack_tiled32_f32).  Pixels x >= W are padding. */
 } magnet_src_layout;
 
 /* Kernel selection (for parity cross-checks and profiling). */
@@ -55,7 +57,9 @@ typedef enum magnet_variant {
   MAGNET_VARIANT_AUTO = 0,   /* production choice                                              */
   MAGNET_VARIANT_DIRECT = 1, /* one thread per output, 4 taps x C channels per hypothesis,
                                 reference operation order, fp64 view accumulation             */
-  MAGNET_VARIANT_CELLS = 2   /* tap-sharing kernel: per-lane bilinear-cell records             */
+  MAGNET_VARIANT_CELLS = 2,  /* tap-sharing kernel: per-lane bilinear-cell records             */
+  MAGNET_VARIANT_CELLS_NOREUSE = 3 /* diagnostic: as CELLS, but every cell gathers all 4 taps
+                                      (MAGNET_DEPTH_GAUSS only)                                */
 } magnet_variant;
 
 /* Per (batch element, view) camera constants, 16 floats, produced by magnet_pack_cameras_f32.
@@ -118,8 +122,9 @@ int magnet_pack_cameras_f32(const float* intM, const float* R, int64_t r_sb, int
                             const int32_t* is_valid, int32_t B, int32_t V, magnet_camera* cams_out,
                             void* stream);
 
-/* Source-feature repack (N, C, H, W) -> (N, C/4, H, W, 4); C % 4 == 0, dst 16-byte aligned. */
-int magnet_repack_c4hw4_f32(const float* src_nchw, float* dst, int32_t N, int32_t C, int32_t H, int32_t W,
+/* Source-feature repack (N, C, H, W) -> MAGNET_SRC_TILED32 (N, H, ceil(W/32), C/4, 32, 4);
+ * C % 4 == 0, dst 16-byte aligned, padding pixels are written as zeros. */
+int magnet_repack_tiled32_f32(const float* src_nchw, float* dst, int32_t N, int32_t C, int32_t H, int32_t W,
                             void* stream);
 
 /*

@@ -38,20 +38,24 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every .cu for sm_100a and link the shared library.  No-op when up to date."""
+def build(force: bool = False, verbose: bool = False, defines=(), tag: str = "") -> Path:
+    """Compile every .cu for sm_100a and link the shared library.  No-op when up to date.
+    ``defines`` / ``tag`` build a tuning variant (e.g. defines=("MAGNET_NCELL=4",), tag="nc4") into
+    libmagnet_b200_<tag>.so, selectable at run time with the MAGNET_B200_LIB environment variable."""
     BUILD.mkdir(exist_ok=True)
-    stamp = BUILD / "digest.txt"
-    dig = _digest()
-    if not force and LIB.exists() and stamp.exists() and stamp.read_text() == dig:
-        return LIB
+    lib = LIB if not tag else PKG / f"libmagnet_b200_{tag}.so"
+    stamp = BUILD / f"digest{tag}.txt"
+    dig = _digest() + "|" + ",".join(defines)
+    if not force and lib.exists() and stamp.exists() and stamp.read_text() == dig:
+        return lib
     nvcc = _nvcc()
 
     def compile_one(src: str):
-        obj = BUILD / (src + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-I", str(PKG.parent / "include"), "-c", str(CSRC / src), "-o", str(obj)]
+        obj = BUILD / (src + tag + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", str(PKG.parent / "include"), "-c",
+               str(CSRC / src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        (BUILD / (src + ".log")).write_text(r.stdout + r.stderr)
+        (BUILD / (src + tag + ".log")).write_text(r.stdout + r.stderr)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
         if verbose:
@@ -60,13 +64,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs)]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(lib), *map(str, objs)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     stamp.write_text(dig)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

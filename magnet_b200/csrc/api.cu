@@ -8,10 +8,10 @@
 namespace magnet {
 cudaError_t launch_cost_direct(const CostParams& p, int depth_mode, int src_layout, int C, bool cw,
                                bool softmax, cudaStream_t st, int* launches);
-cudaError_t launch_cost_cells(const CostParams& p, int mode, int layout, int C, bool cw, bool softmax,
+cudaError_t launch_cost_cells(const CostParams& p, int mode, int C, bool cw, bool softmax, bool reuse,
                               cudaStream_t st, int* launches);
-bool cells_supports(int C, int D);
-void cells_launch_info(int B, int HW, int D, int* grid, int* block, int* smem);
+bool cells_supports(int C, int D, int layout, bool softmax);
+void cells_launch_info(int B, int HW, int D, bool softmax, int* grid, int* block, int* smem);
 cudaError_t launch_pack_cameras(const float* intM, const float* R, int64_t r_sb, int64_t r_sv, int64_t r_si,
                                 int64_t r_sj, const float* t, int64_t t_sb, int64_t t_sv, int64_t t_si,
                                 const int32_t* is_valid, int B, int V, magnet_camera* out, cudaStream_t st);
@@ -46,22 +46,23 @@ int validate_cost(const magnet_cost_args* a) {
     case MAGNET_DEPTH_PLANES: if (!a->k_host) return MAGNET_ERR_NULL; break;
     default: return MAGNET_ERR_UNSUPPORTED;
   }
-  if (a->src_layout == MAGNET_SRC_C4HW4) {
+  if (a->src_layout == MAGNET_SRC_TILED32) {
     if (a->C % 4 != 0) return MAGNET_ERR_UNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(a->src_feat) % 16 != 0) return MAGNET_ERR_ALIGN;
   } else if (a->src_layout != MAGNET_SRC_NCHW) {
     return MAGNET_ERR_UNSUPPORTED;
   }
-  if (a->variant != MAGNET_VARIANT_AUTO && a->variant != MAGNET_VARIANT_DIRECT &&
-      a->variant != MAGNET_VARIANT_CELLS)
+  if (a->variant < MAGNET_VARIANT_AUTO || a->variant > MAGNET_VARIANT_CELLS_NOREUSE) return MAGNET_ERR_UNSUPPORTED;
+  if ((a->variant == MAGNET_VARIANT_CELLS || a->variant == MAGNET_VARIANT_CELLS_NOREUSE) &&
+      !magnet::cells_supports(a->C, a->D, a->src_layout, a->softmax != 0))
     return MAGNET_ERR_UNSUPPORTED;
-  if (a->variant == MAGNET_VARIANT_CELLS && !magnet::cells_supports(a->C, a->D)) return MAGNET_ERR_UNSUPPORTED;
+  if (a->variant == MAGNET_VARIANT_CELLS_NOREUSE && a->depth_mode != MAGNET_DEPTH_GAUSS) return MAGNET_ERR_UNSUPPORTED;
   return MAGNET_OK;
 }
 
 bool use_cells(const magnet_cost_args* a) {
   if (a->variant == MAGNET_VARIANT_DIRECT) return false;
-  return magnet::cells_supports(a->C, a->D);
+  return magnet::cells_supports(a->C, a->D, a->src_layout, a->softmax != 0);
 }
 }  // namespace
 
@@ -90,7 +91,7 @@ int magnet_cost_launch_info(const magnet_cost_args* a, int* grid_ctas, int* bloc
   if (st != MAGNET_OK) return st;
   if (!grid_ctas || !block_threads || !smem_bytes) return MAGNET_ERR_NULL;
   if (use_cells(a)) {
-    magnet::cells_launch_info(a->B, a->H * a->W, a->D, grid_ctas, block_threads, smem_bytes);
+    magnet::cells_launch_info(a->B, a->H * a->W, a->D, a->softmax != 0, grid_ctas, block_threads, smem_bytes);
   } else {
     *grid_ctas = ((a->H * a->W + 127) / 128) * a->D * a->B;
     *block_threads = 128;
@@ -114,8 +115,8 @@ int magnet_cost_volume_f32(const magnet_cost_args* a, void* stream) {
   int launches = 0;
   cudaError_t e;
   if (use_cells(a))
-    e = magnet::launch_cost_cells(p, a->depth_mode, a->src_layout, a->C, a->consistency != 0, a->softmax != 0,
-                                  (cudaStream_t)stream, &launches);
+    e = magnet::launch_cost_cells(p, a->depth_mode, a->C, a->consistency != 0, a->softmax != 0,
+                                  a->variant != MAGNET_VARIANT_CELLS_NOREUSE, (cudaStream_t)stream, &launches);
   else
     e = magnet::launch_cost_direct(p, a->depth_mode, a->src_layout, a->C, a->consistency != 0, a->softmax != 0,
                                    (cudaStream_t)stream, &launches);
@@ -137,7 +138,7 @@ int magnet_pack_cameras_f32(const float* intM, const float* R, int64_t r_sb, int
   return MAGNET_OK;
 }
 
-int magnet_repack_c4hw4_f32(const float* src_nchw, float* dst, int32_t N, int32_t C, int32_t H, int32_t W,
+int magnet_repack_tiled32_f32(const float* src_nchw, float* dst, int32_t N, int32_t C, int32_t H, int32_t W,
                             void* stream) {
   if (!src_nchw || !dst) return MAGNET_ERR_NULL;
   if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return MAGNET_ERR_SHAPE;

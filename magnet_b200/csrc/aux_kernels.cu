@@ -32,19 +32,25 @@ __global__ void pack_cameras_kernel(const float* __restrict__ intM, const float*
   out[idx] = c;
 }
 
-// (N, C, H, W) -> (N, C/4, H, W, 4).  One thread per (n, c4, pixel): 4 coalesced 4-byte reads
-// (stride HW), one coalesced 16-byte write.
-__global__ void repack_c4hw4_kernel(const float* __restrict__ src, float4* __restrict__ dst, int C4, int HW) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= HW) return;
-  const size_t img = blockIdx.z, c4 = blockIdx.y;
-  const float* s = src + (img * C4 * 4 + c4 * 4) * HW + n;
-  float4 o;
-  o.x = s[0];
-  o.y = s[(size_t)HW];
-  o.z = s[2 * (size_t)HW];
-  o.w = s[3 * (size_t)HW];
-  dst[(img * C4 + c4) * HW + n] = o;
+// (N, C, H, W) -> TILED32 (N, H, XB, C/4, 32, 4), XB = ceil(W/32).  One thread per (n, y, xb, c4, xi):
+// 4 coalesced 4-byte reads (stride HW) along x, one coalesced 16-byte write; padding pixels get zeros.
+__global__ void repack_tiled32_kernel(const float* __restrict__ src, float4* __restrict__ dst, int C4, int H,
+                                      int W, int XB) {
+  const int xi = threadIdx.x, c4 = threadIdx.y + blockIdx.z % ((C4 + 3) / 4) * 4;
+  const int xb = blockIdx.x, y = blockIdx.y;
+  const size_t img = blockIdx.z / ((C4 + 3) / 4);
+  if (c4 >= C4) return;
+  const int x = xb * 32 + xi;
+  const size_t HW = (size_t)H * W;
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (x < W) {
+    const float* s = src + (img * C4 * 4 + (size_t)c4 * 4) * HW + (size_t)y * W + x;
+    o.x = s[0];
+    o.y = s[HW];
+    o.z = s[2 * HW];
+    o.w = s[3 * HW];
+  }
+  dst[(((img * H + y) * XB + xb) * C4 + c4) * 32 + xi] = o;
 }
 
 struct KParams {
@@ -98,9 +104,9 @@ cudaError_t launch_pack_cameras(const float* intM, const float* R, int64_t r_sb,
 }
 
 cudaError_t launch_repack(const float* src, float* dst, int N, int C, int H, int W, cudaStream_t st) {
-  const int HW = H * W;
-  dim3 grid((HW + 255) / 256, C / 4, N);
-  repack_c4hw4_kernel<<<grid, 256, 0, st>>>(src, reinterpret_cast<float4*>(dst), C / 4, HW);
+  const int C4 = C / 4, XB = (W + 31) / 32;
+  dim3 grid(XB, H, N * ((C4 + 3) / 4)), block(32, 4);
+  repack_tiled32_kernel<<<grid, block, 0, st>>>(src, reinterpret_cast<float4*>(dst), C4, H, W, XB);
   return cudaGetLastError();
 }
 

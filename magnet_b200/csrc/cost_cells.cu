@@ -9,36 +9,52 @@
 // sigma); every hypothesis inside the cell is then a 3-FMA bilinear polynomial per quantity.
 //
 // Mapping: one thread per reference pixel (a warp = 32 consecutive pixels of a row, so source
-// gathers of neighbouring lanes hit neighbouring addresses), loop over views inside the thread.
-// Per (pixel, view) the work is split into three phases that every lane of a warp executes in
-// LOCKSTEP — a run-per-cell loop would diverge 2.2x on the bench workload (measured by
-// simulation):
+// gathers of neighbouring lanes hit neighbouring addresses), loops over hypothesis chunks and views
+// inside the thread.  Per (pixel, chunk, view) the work is split into three phases that every lane
+// of a warp executes in LOCKSTEP — a run-per-cell loop would diverge 2.2x on the bench workload
+// (measured by simulation):
 //   A  walk the hypotheses j in order, record every change of bilinear cell -> per-lane cell list
 //      (headers in shared memory, at most NCELL per round);
-//   B  for cell i = 0..warp-max: 4 x C-channel dot products + mu/sigma taps -> 12 polynomial
-//      coefficients per cell, stored as 3 float4 per lane in shared memory;
+//   B  for cell i = 0..warp-max: channel dot products + mu/sigma taps of the taps that are NEW with
+//      respect to the lane's previous cell (an edge-adjacent cell shares two taps, kept in
+//      registers) -> 12 polynomial coefficients per cell, 3 float4 per lane in shared memory;
 //   C  walk the hypotheses again; on leaving the current cell reload the next record (3 LDS.128,
 //      the only divergent code), evaluate cost / mu~ / sigma~, apply the consistency test and
 //      accumulate over views in a shared-memory column owned by the lane.
 // If a lane needs more than NCELL cells (incoherent depth, e.g. random test inputs) the warp
 // processes the hypotheses in several rounds [j_lo, j_end), j_end = warp-min of the first
 // hypothesis a lane could not record — always correct, no separate slow path.
+// Hypotheses are accumulated in chunks of JCHUNK so the accumulator column stays small
+// (16 KB per CTA) and 4 CTAs (16 warps) fit per SM; the softmax variant keeps all D planes.
+//
+// Source features are gathered from the TILED32 layout (N, H, W/32, C/4, 32, 4): the 16 channel
+// quads of one pixel sit at a compile-time stride (512 B), so one base address + immediates serve
+// the whole dot product, and 32 neighbouring pixels form one contiguous 512-byte segment per quad.
 //
 // Numerics (DESIGN.md "parity"): same formulas as the reference, but (i) 1/Zp via MUFU.RCP + one
 // Newton step and ix = P0/Zp - 0.5 folded into one FMA instead of the normalise / clamp /
-// unnormalise round trip, (ii) channel sums re-associated (dot-then-blend), (iii) bilinear
-// polynomial instead of 4 explicit weights, (iv) fp32 view accumulation.  Each changes results at
-// the 1e-6 relative level; the hard consistency threshold can flip for elements within ~1e-6 of it.
+// unnormalise round trip, (ii) channel sums re-associated (dot-then-blend, packed f32x2 FMAs),
+// (iii) bilinear polynomial instead of 4 explicit weights, (iv) fp32 view accumulation.  Each
+// changes results at the 1e-6 relative level; the hard consistency threshold can flip for elements
+// within ~1e-5 of it (the reference's own fp32-vs-fp64 flips have the same margins).
 #include "common.cuh"
 
 namespace magnet {
 
-constexpr int NT = 128;    // threads per CTA = reference pixels per CTA
-constexpr int NCELL = 8;   // cell records per lane per round
+#ifndef MAGNET_NCELL
+#define MAGNET_NCELL 5
+#endif
+#ifndef MAGNET_JCHUNK
+#define MAGNET_JCHUNK 32
+#endif
+constexpr int NT = 128;                // threads per CTA = reference pixels per CTA
+constexpr int NCELL = MAGNET_NCELL;    // cell records per lane per round
+constexpr int JCHUNK = MAGNET_JCHUNK;  // hypotheses per accumulation chunk (non-softmax variants)
 
-// dynamic shared memory: rec[NCELL][3][NT] float4 | hdr[NCELL][NT] float2 | acc[D][NT] float
-__host__ __device__ inline size_t cells_smem_bytes(int D) {
-  return (size_t)NCELL * 3 * NT * 16 + (size_t)NCELL * NT * 8 + (size_t)D * NT * 4;
+__host__ __device__ inline int cells_chunk(int D, bool softmax) { return softmax ? D : (D < JCHUNK ? D : JCHUNK); }
+// dynamic shared memory: rec[NCELL][3][NT] float4 | hdr[NCELL][NT] float2 | acc[chunk][NT] float
+__host__ __device__ inline size_t cells_smem_bytes(int D, bool softmax) {
+  return (size_t)NCELL * 3 * NT * 16 + (size_t)NCELL * NT * 8 + (size_t)cells_chunk(D, softmax) * NT * 4;
 }
 
 template <int MODE>
@@ -71,52 +87,65 @@ __device__ __forceinline__ void project(const CostParams& p, const DepthSrc<MODE
   iy = fminf(fmaxf(iy, -2.0f), ymax);
 }
 
-template <int C, int LAYOUT>
-__device__ __forceinline__ float tap_dot(const float* __restrict__ src_img, const float (&ref)[C], int off,
-                                         int HW) {
-  float s0 = 0.0f, s1 = 0.0f;
-  if (LAYOUT == MAGNET_SRC_C4HW4) {
-    const float4* s = reinterpret_cast<const float4*>(src_img) + off;
+// <ref, src[tap]> over C channels: C/4 LDG.128 at immediate offsets from one address, packed FMAs.
+template <int C>
+__device__ __forceinline__ float tap_dot(const float4* __restrict__ s, const float2 (&ref2)[C / 2]) {
+  float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int c4 = 0; c4 < C / 4; ++c4) {
-      const float4 t = __ldg(s + (size_t)c4 * HW);
-      s0 = __fmaf_rn(ref[4 * c4 + 0], t.x, s0);
-      s1 = __fmaf_rn(ref[4 * c4 + 1], t.y, s1);
-      s0 = __fmaf_rn(ref[4 * c4 + 2], t.z, s0);
-      s1 = __fmaf_rn(ref[4 * c4 + 3], t.w, s1);
-    }
-  } else {
-    const float* s = src_img + off;
-#pragma unroll
-    for (int c = 0; c < C; c += 2) {
-      s0 = __fmaf_rn(ref[c], ldg_f(s + (size_t)c * HW), s0);
-      s1 = __fmaf_rn(ref[c + 1], ldg_f(s + (size_t)(c + 1) * HW), s1);
-    }
+  for (int c4 = 0; c4 < C / 4; ++c4) {
+    const float4 t = __ldg(s + c4 * 32);
+    s0 = __ffma2_rn(ref2[2 * c4 + 0], make_float2(t.x, t.y), s0);
+    s1 = __ffma2_rn(ref2[2 * c4 + 1], make_float2(t.z, t.w), s1);
   }
-  return s0 + s1;
+  return (s0.x + s0.y) + (s1.x + s1.y);
 }
 
-template <int C, int MODE, int LAYOUT, bool CW, bool SOFTMAX>
-__global__ void __launch_bounds__(NT)
+struct Tap {
+  float f, m, s;   // <ref, src>, source mu, source sigma at one integer source pixel (0 when outside)
+};
+
+template <int C, bool CW>
+__device__ __forceinline__ Tap load_tap(const float4* __restrict__ src_img, const float* __restrict__ gm,
+                                        const float2 (&ref2)[C / 2], int x, int y, int W, int H, int XB, int HW) {
+  Tap t;
+  t.f = t.m = t.s = 0.0f;
+  if (x >= 0 && x < W && y >= 0 && y < H) {
+    t.f = tap_dot<C>(src_img + ((y * XB + (x >> 5)) * (C / 4) * 32 + (x & 31)), ref2);
+    if (CW) {
+      t.m = ldg_f(gm + y * W + x);
+      t.s = ldg_f(gm + HW + y * W + x);
+    }
+  }
+  return t;
+}
+
+__device__ __forceinline__ float4 bilinear_poly(float v00, float v01, float v10, float v11) {
+  // v(fx,fy) = c0 + fx*cx + fy*(cy + fx*cxy)
+  return make_float4(v00, v01 - v00, v10 - v00, (v00 - v01) - (v10 - v11));
+}
+
+template <int C, int MODE, bool CW, bool SOFTMAX, bool REUSE>
+__global__ void __launch_bounds__(NT, 4)
 cost_cells_kernel(const __grid_constant__ CostParams p) {
   extern __shared__ float4 smem4[];
   float4* rec = smem4;                                                   // [NCELL][3][NT]
   float2* hdr = reinterpret_cast<float2*>(smem4 + NCELL * 3 * NT);       // [NCELL][NT]
-  float* acc = reinterpret_cast<float*>(hdr + NCELL * NT);               // [D][NT]
+  float* acc = reinterpret_cast<float*>(hdr + NCELL * NT);               // [chunk][NT]
 
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
   const int H = p.H, W = p.W, HW = p.HW, D = p.D;
+  const int XB = (W + 31) >> 5;
   const int n_raw = blockIdx.x * NT + tid;
   const bool live = n_raw < HW;
   const int n = live ? n_raw : HW - 1;          // dead lanes shadow the last pixel, never store
   const unsigned FULL = 0xffffffffu;
 
-  float ref[C];
+  float2 ref2[C / 2];
   {
     const float* rp = p.ref_feat + (size_t)b * C * HW + n;
 #pragma unroll
-    for (int c = 0; c < C; ++c) ref[c] = ldg_f(rp + (size_t)c * HW);
+    for (int c = 0; c < C / 2; ++c) ref2[c] = make_float2(ldg_f(rp + (size_t)(2 * c) * HW), ldg_f(rp + (size_t)(2 * c + 1) * HW));
   }
   const float r0 = ldg_f(p.rays + ((size_t)b * 3 + 0) * HW + n);
   const float r1 = ldg_f(p.rays + ((size_t)b * 3 + 1) * HW + n);
@@ -131,143 +160,170 @@ cost_cells_kernel(const __grid_constant__ CostParams p) {
     ds.mu = ldg_f(p.ref_gmm + ((size_t)b * 2 + 0) * HW + n);
     ds.sg = ldg_f(p.ref_gmm + ((size_t)b * 2 + 1) * HW + n);
   }
-  for (int j = 0; j < D; ++j) acc[j * NT + tid] = 0.0f;
-
   const float xmax = (float)W + 1.0f, ymax = (float)H + 1.0f;
+  const int chunk = cells_chunk(D, SOFTMAX);
+  const size_t img_stride4 = (size_t)H * XB * (C / 4) * 32;             // float4 per source image
 
-  for (int v = 0; v < p.V; ++v) {
-    const magnet_camera* cam = p.cams + (b * p.V + v);
-    if (cam->valid != 1.0f) continue;                                    // CTA-uniform
-    const float a0 = cam->a[0], a1 = cam->a[1], a2 = cam->a[2];
-    const float q0 = __fmaf_rn(cam->A[2], r2, __fmaf_rn(cam->A[1], r1, __fmul_rn(cam->A[0], r0)));
-    const float q1 = __fmaf_rn(cam->A[5], r2, __fmaf_rn(cam->A[4], r1, __fmul_rn(cam->A[3], r0)));
-    const float q2 = __fmaf_rn(cam->A[8], r2, __fmaf_rn(cam->A[7], r1, __fmul_rn(cam->A[6], r0)));
-    const int vb = v * p.B + b;
-    const float* src_img = p.src_feat + (size_t)vb * C * HW;
-    const float* gm = CW ? p.src_gmm + (size_t)vb * 2 * HW : nullptr;
+  for (int jc = 0; jc < D; jc += chunk) {
+    const int jc_end = min(jc + chunk, D);
+    for (int j = 0; j < jc_end - jc; ++j) acc[j * NT + tid] = 0.0f;
 
-    int j_lo = 0;
-    while (j_lo < D) {                                                   // rounds; warp-uniform
-      // ---------------- phase A: cell list --------------------------------------------------
-      int ncell = 0, j_stop = D;
-      {
-        float cx = -1e30f, cy = -1e30f;
-        for (int j = j_lo; j < D; ++j) {
-          float ix, iy, z;
-          project<MODE>(p, ds, j, a0, a1, a2, q0, q1, q2, xmax, ymax, ix, iy, z);
-          const float fx = ix - cx, fy = iy - cy;
-          if (!(fx >= 0.0f && fx < 1.0f && fy >= 0.0f && fy < 1.0f)) {
-            if (ncell == NCELL) { j_stop = j; break; }
-            cx = floorf(ix);
-            cy = floorf(iy);
-            hdr[ncell * NT + tid] = make_float2(cx, cy);
-            ++ncell;
-          }
-        }
-      }
-      const int j_end = __reduce_min_sync(FULL, j_stop);
-      const int nmax = __reduce_max_sync(FULL, ncell);
+    for (int v = 0; v < p.V; ++v) {
+      const magnet_camera* cam = p.cams + (b * p.V + v);
+      if (cam->valid != 1.0f) continue;                                  // CTA-uniform
+      const float a0 = cam->a[0], a1 = cam->a[1], a2 = cam->a[2];
+      const float q0 = __fmaf_rn(cam->A[2], r2, __fmaf_rn(cam->A[1], r1, __fmul_rn(cam->A[0], r0)));
+      const float q1 = __fmaf_rn(cam->A[5], r2, __fmaf_rn(cam->A[4], r1, __fmul_rn(cam->A[3], r0)));
+      const float q2 = __fmaf_rn(cam->A[8], r2, __fmaf_rn(cam->A[7], r1, __fmul_rn(cam->A[6], r0)));
+      const int vb = v * p.B + b;
+      const float4* src_img = reinterpret_cast<const float4*>(p.src_feat) + (size_t)vb * img_stride4;
+      const float* gm = CW ? p.src_gmm + (size_t)vb * 2 * HW : nullptr;
 
-      // ---------------- phase B: per-cell records -------------------------------------------
-      for (int i = 0; i < nmax; ++i) {
-        if (i < ncell) {
-          const float2 h = hdr[i * NT + tid];
-          const int x0 = (int)h.x, y0 = (int)h.y, x1 = x0 + 1, y1 = y0 + 1;
-          const bool xin0 = x0 >= 0 && x0 < W, xin1 = x1 >= 0 && x1 < W;
-          const bool yin0 = y0 >= 0 && y0 < H, yin1 = y1 >= 0 && y1 < H;
-          const int o00 = y0 * W + x0;
-          float v00 = 0.f, v01 = 0.f, v10 = 0.f, v11 = 0.f;
-          if (xin0 && yin0) v00 = tap_dot<C, LAYOUT>(src_img, ref, o00, HW);
-          if (xin1 && yin0) v01 = tap_dot<C, LAYOUT>(src_img, ref, o00 + 1, HW);
-          if (xin0 && yin1) v10 = tap_dot<C, LAYOUT>(src_img, ref, o00 + W, HW);
-          if (xin1 && yin1) v11 = tap_dot<C, LAYOUT>(src_img, ref, o00 + W + 1, HW);
-          // bilinear polynomial  v(fx,fy) = c0 + fx*cx + fy*(cy + fx*cxy)
-          rec[(i * 3 + 0) * NT + tid] = make_float4(v00, v01 - v00, v10 - v00, (v00 - v01) - (v10 - v11));
-          if (CW) {
-            float m00 = 0.f, m01 = 0.f, m10 = 0.f, m11 = 0.f, s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
-            if (xin0 && yin0) { m00 = ldg_f(gm + o00); s00 = ldg_f(gm + HW + o00); }
-            if (xin1 && yin0) { m01 = ldg_f(gm + o00 + 1); s01 = ldg_f(gm + HW + o00 + 1); }
-            if (xin0 && yin1) { m10 = ldg_f(gm + o00 + W); s10 = ldg_f(gm + HW + o00 + W); }
-            if (xin1 && yin1) { m11 = ldg_f(gm + o00 + W + 1); s11 = ldg_f(gm + HW + o00 + W + 1); }
-            rec[(i * 3 + 1) * NT + tid] = make_float4(m00, m01 - m00, m10 - m00, (m00 - m01) - (m10 - m11));
-            rec[(i * 3 + 2) * NT + tid] = make_float4(s00, s01 - s00, s10 - s00, (s00 - s01) - (s10 - s11));
-          }
-        }
-      }
+      // previous cell of this lane (taps kept in registers for reuse by an edge-adjacent next cell)
+      int px0 = -1000000, py0 = -1000000;
+      Tap p00, p01, p10, p11;
+      p00.f = p00.m = p00.s = 0.f;
+      p01 = p10 = p11 = p00;
 
-      // ---------------- phase C: evaluate hypotheses [j_lo, j_end) ---------------------------
-      {
-        int i = -1;
-        float cx = -1e30f, cy = -1e30f;
-        float4 rd = make_float4(0.f, 0.f, 0.f, 0.f), rm = rd, rs = rd;
+      int j_lo = jc;
+      while (j_lo < jc_end) {                                            // rounds; warp-uniform
+        // ---------------- phase A: cell list ------------------------------------------------
+        int ncell = 0, j_stop = jc_end;
+        {
+          float cx = -1e30f, cy = -1e30f;
+          float2* hp = hdr + tid;
 #pragma unroll 2
-        for (int j = j_lo; j < j_end; ++j) {
-          float ix, iy, z;
-          project<MODE>(p, ds, j, a0, a1, a2, q0, q1, q2, xmax, ymax, ix, iy, z);
-          float fx = ix - cx, fy = iy - cy;
-          if (!(fx >= 0.0f && fx < 1.0f && fy >= 0.0f && fy < 1.0f)) {
-            ++i;
-            const float2 h = hdr[i * NT + tid];
-            cx = h.x;
-            cy = h.y;
-            rd = rec[(i * 3 + 0) * NT + tid];
-            if (CW) {
-              rm = rec[(i * 3 + 1) * NT + tid];
-              rs = rec[(i * 3 + 2) * NT + tid];
+          for (int j = j_lo; j < jc_end; ++j) {
+            float ix, iy, z;
+            project<MODE>(p, ds, j, a0, a1, a2, q0, q1, q2, xmax, ymax, ix, iy, z);
+            const float fx = ix - cx, fy = iy - cy;
+            if (!(fx >= 0.0f && fx < 1.0f && fy >= 0.0f && fy < 1.0f)) {
+              if (ncell == NCELL) { j_stop = j; break; }
+              cx = floorf(ix);
+              cy = floorf(iy);
+              *hp = make_float2(cx, cy);
+              hp += NT;
+              ++ncell;
             }
-            fx = ix - cx;
-            fy = iy - cy;
           }
-          const float cost = __fmaf_rn(fy, __fmaf_rn(fx, rd.w, rd.z), __fmaf_rn(fx, rd.y, rd.x));
-          float val = cost;
-          if (CW) {
-            const float mu = __fmaf_rn(fy, __fmaf_rn(fx, rm.w, rm.z), __fmaf_rn(fx, rm.y, rm.x));
-            const float sg = __fmaf_rn(fy, __fmaf_rn(fx, rs.w, rs.z), __fmaf_rn(fx, rs.y, rs.x));
-            // homography.py:157-158: |z - mu~| < sigma~ * kappa, strict
-            val = (fabsf(__fsub_rn(z, mu)) < __fmul_rn(sg, p.kappa)) ? cost : 0.0f;
+        }
+        const int j_end = __reduce_min_sync(FULL, j_stop);
+        const int nmax = __reduce_max_sync(FULL, ncell);
+
+        // ---------------- phase B: per-cell records ------------------------------------------
+        for (int i = 0; i < nmax; ++i) {
+          if (i < ncell) {
+            const float2 h = hdr[i * NT + tid];
+            const int x0 = (int)h.x, y0 = (int)h.y;
+            const int dx = x0 - px0, dy = y0 - py0;
+            const bool mvx = REUSE && dy == 0 && (dx == 1 || dx == -1);
+            const bool mvy = REUSE && dx == 0 && (dy == 1 || dy == -1);
+            // two taps every lane computes: the new column (x move), the new row (y move), or the top row
+            int ax = x0, ay = y0, bx = x0 + 1, by = y0;
+            if (mvx) { ax = bx = (dx == 1) ? x0 + 1 : x0; by = y0 + 1; }
+            if (mvy) { ay = by = (dy == 1) ? y0 + 1 : y0; }
+            const Tap tA = load_tap<C, CW>(src_img, gm, ref2, ax, ay, W, H, XB, HW);
+            const Tap tB = load_tap<C, CW>(src_img, gm, ref2, bx, by, W, H, XB, HW);
+            Tap n00, n01, n10, n11;
+            if (mvx) {
+              if (dx == 1) { n00 = p01; n10 = p11; n01 = tA; n11 = tB; }
+              else         { n01 = p00; n11 = p10; n00 = tA; n10 = tB; }
+            } else if (mvy) {
+              if (dy == 1) { n00 = p10; n01 = p11; n10 = tA; n11 = tB; }
+              else         { n10 = p00; n11 = p01; n00 = tA; n01 = tB; }
+            } else {                                                     // first cell / diagonal / jump
+              n00 = tA; n01 = tB;
+              n10 = load_tap<C, CW>(src_img, gm, ref2, x0, y0 + 1, W, H, XB, HW);
+              n11 = load_tap<C, CW>(src_img, gm, ref2, x0 + 1, y0 + 1, W, H, XB, HW);
+            }
+            p00 = n00; p01 = n01; p10 = n10; p11 = n11;
+            px0 = x0; py0 = y0;
+            rec[(i * 3 + 0) * NT + tid] = bilinear_poly(n00.f, n01.f, n10.f, n11.f);
+            if (CW) {
+              rec[(i * 3 + 1) * NT + tid] = bilinear_poly(n00.m, n01.m, n10.m, n11.m);
+              rec[(i * 3 + 2) * NT + tid] = bilinear_poly(n00.s, n01.s, n10.s, n11.s);
+            }
           }
-          acc[j * NT + tid] += val;
+        }
+
+        // ---------------- phase C: evaluate hypotheses [j_lo, j_end) -------------------------
+        {
+          float cx = -1e30f, cy = -1e30f;
+          float4 rd = make_float4(0.f, 0.f, 0.f, 0.f), rm = rd, rs = rd;
+          const float2* hp = hdr + tid - NT;
+          const float4* rp = rec + tid - 3 * NT;
+          float* ap = acc + (j_lo - jc) * NT + tid;
+#pragma unroll 2
+          for (int j = j_lo; j < j_end; ++j, ap += NT) {
+            float ix, iy, z;
+            project<MODE>(p, ds, j, a0, a1, a2, q0, q1, q2, xmax, ymax, ix, iy, z);
+            float fx = ix - cx, fy = iy - cy;
+            if (!(fx >= 0.0f && fx < 1.0f && fy >= 0.0f && fy < 1.0f)) {
+              hp += NT;
+              rp += 3 * NT;
+              const float2 h = *hp;
+              cx = h.x;
+              cy = h.y;
+              rd = rp[0];
+              if (CW) {
+                rm = rp[NT];
+                rs = rp[2 * NT];
+              }
+              fx = ix - cx;
+              fy = iy - cy;
+            }
+            const float cost = __fmaf_rn(fy, __fmaf_rn(fx, rd.w, rd.z), __fmaf_rn(fx, rd.y, rd.x));
+            float val = cost;
+            if (CW) {
+              const float mu = __fmaf_rn(fy, __fmaf_rn(fx, rm.w, rm.z), __fmaf_rn(fx, rm.y, rm.x));
+              const float sg = __fmaf_rn(fy, __fmaf_rn(fx, rs.w, rs.z), __fmaf_rn(fx, rs.y, rs.x));
+              // homography.py:157-158: |z - mu~| < sigma~ * kappa, strict
+              val = (fabsf(__fsub_rn(z, mu)) < __fmul_rn(sg, p.kappa)) ? cost : 0.0f;
+            }
+            *ap += val;
+          }
+        }
+        j_lo = j_end;
+      }
+    }
+
+    // -------- chunk epilogue: 1/V mean over ALL views (homography.py:120), optional softmax ------
+    float* outp = p.out + ((size_t)b * D + jc) * HW + n;
+    const int cnt = jc_end - jc;
+    if (!SOFTMAX) {
+      if (live) {
+        if (p.inv_v_exact != 0.0f) {
+          for (int j = 0; j < cnt; ++j) outp[(size_t)j * HW] = acc[j * NT + tid] * p.inv_v_exact;
+        } else {
+          for (int j = 0; j < cnt; ++j) outp[(size_t)j * HW] = __fdiv_rn(acc[j * NT + tid], p.vf);
         }
       }
-      j_lo = j_end;
-    }
-  }
-
-  // ---------------- epilogue: 1/V mean over ALL views (homography.py:120), optional softmax -----
-  float* outp = p.out + (size_t)b * D * HW + n;
-  if (!SOFTMAX) {
-    if (live) {
-      if (p.inv_v_exact != 0.0f) {
-        for (int j = 0; j < D; ++j) outp[(size_t)j * HW] = acc[j * NT + tid] * p.inv_v_exact;
-      } else {
-        for (int j = 0; j < D; ++j) outp[(size_t)j * HW] = __fdiv_rn(acc[j * NT + tid], p.vf);
+    } else {                                                             // chunk == D here
+      float m = -INFINITY;
+      for (int j = 0; j < cnt; ++j) {
+        const float x = __fdiv_rn(acc[j * NT + tid], p.vf);
+        acc[j * NT + tid] = x;
+        m = fmaxf(m, x);
       }
+      float s = 0.0f;
+      for (int j = 0; j < cnt; ++j) {
+        const float e = expf(acc[j * NT + tid] - m);
+        acc[j * NT + tid] = e;
+        s += e;
+      }
+      if (live)
+        for (int j = 0; j < cnt; ++j) outp[(size_t)j * HW] = __fdiv_rn(acc[j * NT + tid], s);
     }
-  } else {
-    float m = -INFINITY;
-    for (int j = 0; j < D; ++j) {
-      const float x = __fdiv_rn(acc[j * NT + tid], p.vf);
-      acc[j * NT + tid] = x;
-      m = fmaxf(m, x);
-    }
-    float s = 0.0f;
-    for (int j = 0; j < D; ++j) {
-      const float e = expf(acc[j * NT + tid] - m);
-      acc[j * NT + tid] = e;
-      s += e;
-    }
-    if (live)
-      for (int j = 0; j < D; ++j) outp[(size_t)j * HW] = __fdiv_rn(acc[j * NT + tid], s);
   }
 }
 
-template <int C, int MODE, int LAYOUT>
-static cudaError_t launch_cml(const CostParams& p, bool cw, bool softmax, cudaStream_t st) {
-  const size_t smem = cells_smem_bytes(p.D);
+template <int C, int MODE, bool REUSE>
+static cudaError_t launch_cm(const CostParams& p, bool cw, bool softmax, cudaStream_t st) {
+  const size_t smem = cells_smem_bytes(p.D, softmax);
   dim3 grid((p.HW + NT - 1) / NT, p.B), block(NT);
 #define MAGNET_LAUNCH(CWv, SMv)                                                                         \
   do {                                                                                                  \
-    auto kern = cost_cells_kernel<C, MODE, LAYOUT, CWv, SMv>;                                           \
+    auto kern = cost_cells_kernel<C, MODE, CWv, SMv, REUSE>;                                            \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                     \
     kern<<<grid, block, smem, st>>>(p);                                                                 \
@@ -281,34 +337,34 @@ static cudaError_t launch_cml(const CostParams& p, bool cw, bool softmax, cudaSt
 }
 
 template <int C>
-static cudaError_t launch_c(const CostParams& p, int mode, int layout, bool cw, bool softmax, cudaStream_t st) {
-  if (layout == MAGNET_SRC_C4HW4) {
-    if (mode == MAGNET_DEPTH_VOLUME) return launch_cml<C, MAGNET_DEPTH_VOLUME, MAGNET_SRC_C4HW4>(p, cw, softmax, st);
-    if (mode == MAGNET_DEPTH_GAUSS) return launch_cml<C, MAGNET_DEPTH_GAUSS, MAGNET_SRC_C4HW4>(p, cw, softmax, st);
-    return launch_cml<C, MAGNET_DEPTH_PLANES, MAGNET_SRC_C4HW4>(p, cw, softmax, st);
+static cudaError_t launch_c(const CostParams& p, int mode, bool cw, bool softmax, bool reuse, cudaStream_t st) {
+  if (!reuse) {   // diagnostic variant: only the bench configuration is instantiated
+    if (mode == MAGNET_DEPTH_GAUSS) return launch_cm<C, MAGNET_DEPTH_GAUSS, false>(p, cw, softmax, st);
+    return cudaErrorInvalidValue;
   }
-  if (mode == MAGNET_DEPTH_VOLUME) return launch_cml<C, MAGNET_DEPTH_VOLUME, MAGNET_SRC_NCHW>(p, cw, softmax, st);
-  if (mode == MAGNET_DEPTH_GAUSS) return launch_cml<C, MAGNET_DEPTH_GAUSS, MAGNET_SRC_NCHW>(p, cw, softmax, st);
-  return launch_cml<C, MAGNET_DEPTH_PLANES, MAGNET_SRC_NCHW>(p, cw, softmax, st);
+  if (mode == MAGNET_DEPTH_VOLUME) return launch_cm<C, MAGNET_DEPTH_VOLUME, true>(p, cw, softmax, st);
+  if (mode == MAGNET_DEPTH_GAUSS) return launch_cm<C, MAGNET_DEPTH_GAUSS, true>(p, cw, softmax, st);
+  return launch_cm<C, MAGNET_DEPTH_PLANES, true>(p, cw, softmax, st);
 }
 
-bool cells_supports(int C, int D) {
-  return (C == 16 || C == 32 || C == 64) && cells_smem_bytes(D) <= 220 * 1024;
+bool cells_supports(int C, int D, int layout, bool softmax) {
+  return (C == 16 || C == 32 || C == 64) && layout == MAGNET_SRC_TILED32 &&
+         cells_smem_bytes(D, softmax) <= 200 * 1024;
 }
 
-void cells_launch_info(int B, int HW, int D, int* grid, int* block, int* smem) {
+void cells_launch_info(int B, int HW, int D, bool softmax, int* grid, int* block, int* smem) {
   *grid = ((HW + NT - 1) / NT) * B;
   *block = NT;
-  *smem = (int)cells_smem_bytes(D);
+  *smem = (int)cells_smem_bytes(D, softmax);
 }
 
-cudaError_t launch_cost_cells(const CostParams& p, int mode, int layout, int C, bool cw, bool softmax,
+cudaError_t launch_cost_cells(const CostParams& p, int mode, int C, bool cw, bool softmax, bool reuse,
                               cudaStream_t st, int* launches) {
   *launches = 1;
   switch (C) {
-    case 16: return launch_c<16>(p, mode, layout, cw, softmax, st);
-    case 32: return launch_c<32>(p, mode, layout, cw, softmax, st);
-    case 64: return launch_c<64>(p, mode, layout, cw, softmax, st);
+    case 16: return launch_c<16>(p, mode, cw, softmax, reuse, st);
+    case 32: return launch_c<32>(p, mode, cw, softmax, reuse, st);
+    case 64: return launch_c<64>(p, mode, cw, softmax, reuse, st);
     default: return cudaErrorInvalidValue;
   }
 }

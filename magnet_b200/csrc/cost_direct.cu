@@ -86,10 +86,13 @@ cost_direct_kernel(const CostParams p, const int depth_mode, const int src_layou
           cost = __fadd_rn(cost, __fmul_rn(ldg_f(ref + (size_t)c * HW), f));
         }
       } else {
-        const float4* src = reinterpret_cast<const float4*>(p.src_feat) + (size_t)vb * (C / 4) * HW;
-        const int o_nw = y0 * W + x0, o_ne = o_nw + 1, o_sw = o_nw + W, o_se = o_sw + 1;
-        for (int c4 = 0; c4 < C / 4; ++c4) {
-          const float4* s = src + (size_t)c4 * HW;
+        const int XB = (W + 31) >> 5, C4 = C / 4;
+        const float4* src = reinterpret_cast<const float4*>(p.src_feat) + (size_t)vb * H * XB * C4 * 32;
+        // TILED32: pixel (y,x) quad c4 at ((y*XB + x/32)*C4 + c4)*32 + x%32
+        const int o_nw = (y0 * XB + (x0 >> 5)) * C4 * 32 + (x0 & 31), o_ne = (y0 * XB + (x1 >> 5)) * C4 * 32 + (x1 & 31);
+        const int o_sw = (y1 * XB + (x0 >> 5)) * C4 * 32 + (x0 & 31), o_se = (y1 * XB + (x1 >> 5)) * C4 * 32 + (x1 & 31);
+        for (int c4 = 0; c4 < C4; ++c4) {
+          const float4* s = src + c4 * 32;
           float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
           if (in_nw) { const float4 t = __ldg(s + o_nw); f.x = __fmaf_rn(t.x, w_nw, f.x); f.y = __fmaf_rn(t.y, w_nw, f.y); f.z = __fmaf_rn(t.z, w_nw, f.z); f.w = __fmaf_rn(t.w, w_nw, f.w); }
           if (in_ne) { const float4 t = __ldg(s + o_ne); f.x = __fmaf_rn(t.x, w_ne, f.x); f.y = __fmaf_rn(t.y, w_ne, f.y); f.z = __fmaf_rn(t.z, w_ne, f.z); f.w = __fmaf_rn(t.w, w_ne, f.w); }

@@ -99,10 +99,10 @@ def _camera_table(cam_intrins, R, t, is_valid, device):
 def _packed_source(nghbr_feat):
     if nghbr_feat.shape[1] % 4 != 0:
         return nghbr_feat.contiguous(), _lib.SRC_NCHW
-    hit = _cache.get("c4hw4", (nghbr_feat,))
+    hit = _cache.get("tiled32", (nghbr_feat,))
     if hit is None:
-        hit = _cache.put("c4hw4", (nghbr_feat,), ops.repack_c4hw4(nghbr_feat))
-    return hit, _lib.SRC_C4HW4
+        hit = _cache.put("tiled32", (nghbr_feat,), ops.repack_tiled32(nghbr_feat))
+    return hit, _lib.SRC_TILED32
 
 
 def est_costvolume_CW(d_volume, ref_feat, nghbr_feat, ref_gmms, nghbr_gmms,

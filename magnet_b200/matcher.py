@@ -41,7 +41,7 @@ class MatchingPlan:
     device intrinsics / rays, camera-constant table, source features in the gather layout."""
 
     def __init__(self, ref_feat, nghbr_feat, nghbr_gmms, nghbr_poses, is_valid, cam_intrins, *,
-                 thres: int = 5, src_layout: int = _lib.SRC_C4HW4):
+                 thres: int = 5, src_layout: int = _lib.SRC_TILED32):
         dev = ref_feat.device
         self.B, self.C, self.H, self.W = ref_feat.shape
         self.V = nghbr_feat.shape[0] // self.B
@@ -52,8 +52,8 @@ class MatchingPlan:
         intM = cam_intrins['intM'].to(dev, torch.float32).contiguous()
         R, t = nghbr_poses[:, :, :3, :3], nghbr_poses[:, :, :3, 3]
         self.cams = ops.pack_cameras(intM, R, t, is_valid.to(dev, torch.int32))
-        if src_layout == _lib.SRC_C4HW4 and self.C % 4 == 0:
-            self.src, self.layout = ops.repack_c4hw4(nghbr_feat.detach()), _lib.SRC_C4HW4
+        if src_layout == _lib.SRC_TILED32 and self.C % 4 == 0:
+            self.src, self.layout = ops.repack_tiled32(nghbr_feat.detach()), _lib.SRC_TILED32
         else:
             self.src, self.layout = nghbr_feat.detach().contiguous(), _lib.SRC_NCHW
 

@@ -59,14 +59,15 @@ def pack_cameras(intM: torch.Tensor, R: torch.Tensor, t: torch.Tensor, is_valid:
     return cams
 
 
-def repack_c4hw4(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """(N,C,H,W) -> (N,C/4,H,W,4) source-feature layout consumed by the tap-sharing kernel."""
+def repack_tiled32(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(N,C,H,W) -> TILED32 (N, H, ceil(W/32), C/4, 32, 4): the source-feature layout the tap-sharing
+    kernel gathers from (channel quads of a pixel 512 B apart, 32 neighbouring pixels contiguous)."""
     x = _need_cuda_f32("x", x)
     N, Cc, H, W = x.shape
     if out is None:
-        out = torch.empty(N, Cc // 4, H, W, 4, device=x.device, dtype=torch.float32)
-    check(lib().magnet_repack_c4hw4_f32(x.data_ptr(), out.data_ptr(), N, Cc, H, W, _stream()),
-          "magnet_repack_c4hw4_f32")
+        out = torch.empty(N, H, (W + 31) // 32, Cc // 4, 32, 4, device=x.device, dtype=torch.float32)
+    check(lib().magnet_repack_tiled32_f32(x.data_ptr(), out.data_ptr(), N, Cc, H, W, _stream()),
+          "magnet_repack_tiled32_f32")
     return out
 
 
@@ -134,10 +135,9 @@ def cost_launch_info(B, V, D, Cc, H, W, variant=_lib.VARIANT_AUTO):
     """(grid CTAs, threads per CTA, dynamic smem bytes) the cost kernel would use for these sizes."""
     a = CostArgs()
     a.B, a.V, a.D, a.C, a.H, a.W = B, V, D, Cc, H, W
-    a.depth_mode, a.src_layout, a.consistency, a.variant = _lib.DEPTH_PLANES, _lib.SRC_NCHW, 0, variant
-    dummy = (C.c_float * 1)(0.0)
-    one = C.cast(dummy, C.c_void_p)
-    a.ref_feat = a.src_feat = a.rays = a.cams = a.out = a.k_host = one   # validated for non-NULL only
+    a.depth_mode, a.src_layout, a.consistency, a.variant = _lib.DEPTH_PLANES, _lib.SRC_TILED32, 0, variant
+    one = C.c_void_p(0x1000)                       # never dereferenced: validated for non-NULL / alignment only
+    a.ref_feat = a.src_feat = a.rays = a.cams = a.out = a.k_host = one
     g, b, s = C.c_int(), C.c_int(), C.c_int()
     check(lib().magnet_cost_launch_info(C.byref(a), C.byref(g), C.byref(b), C.byref(s)), "magnet_cost_launch_info")
     return g.value, b.value, s.value

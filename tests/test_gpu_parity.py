@@ -86,10 +86,13 @@ def test_fused_sampler_equals_drop_in(cuda):
     drop = magnet_b200.est_costvolume_CW(dvol, g.ref_feat, g.nghbr_feat, g.ref_gmms, g.nghbr_gmms, g.R, g.t,
                                          inp.is_valid, inp.cam_intrins, inp.thres)
     assert torch.equal(fused, drop)
-    nchw = ops.cost_volume(g.ref_feat, g.nghbr_feat, plan.rays, plan.cams, V=inp.V, src_layout=_lib.SRC_NCHW,
-                           consistency=True, src_gmm=g.nghbr_gmms, kappa=5.0, ref_gmm=g.ref_gmms, k=inp.k.tolist(),
-                           variant=_lib.VARIANT_CELLS)
-    assert torch.equal(fused, nchw), "C4HW4 and NCHW gathers must agree exactly"
+    noreuse = plan.cost(g.ref_gmms, inp.k.tolist(), variant=_lib.VARIANT_CELLS_NOREUSE)
+    assert torch.equal(fused, noreuse), "register tap reuse must not change a single bit"
+    d_nchw = ops.cost_volume(g.ref_feat, g.nghbr_feat, plan.rays, plan.cams, V=inp.V, src_layout=_lib.SRC_NCHW,
+                             consistency=True, src_gmm=g.nghbr_gmms, kappa=5.0, ref_gmm=g.ref_gmms, k=inp.k.tolist(),
+                             variant=_lib.VARIANT_DIRECT)
+    d_tiled = plan.cost(g.ref_gmms, inp.k.tolist(), variant=_lib.VARIANT_DIRECT)
+    assert torch.equal(d_nchw, d_tiled), "TILED32 and NCHW gathers must agree exactly"
 
 
 @pytest.mark.parametrize("vname,variant", VARIANTS)

@@ -49,7 +49,7 @@ def test_cost_args_validation_without_gpu():
     a.consistency = 1                                                           # needs src_gmm
     assert L.magnet_cost_volume_f32(C.byref(a), None) == _lib.ERR_NULL
     a.consistency = 0
-    a.src_layout = _lib.SRC_C4HW4
+    a.src_layout = _lib.SRC_TILED32
     a.C = 18
     assert L.magnet_cost_volume_f32(C.byref(a), None) == _lib.ERR_UNSUPPORTED   # C % 4
     a.C = 16
@@ -59,7 +59,7 @@ def test_cost_args_validation_without_gpu():
     a.variant = _lib.VARIANT_CELLS
     a.C = 20
     assert L.magnet_cost_volume_f32(C.byref(a), None) == _lib.ERR_UNSUPPORTED   # cells kernel: C in {16,32,64}
-    assert L.magnet_repack_c4hw4_f32(p, p, 1, 6, 2, 2, None) == _lib.ERR_UNSUPPORTED
+    assert L.magnet_repack_tiled32_f32(p, p, 1, 6, 2, 2, None) == _lib.ERR_UNSUPPORTED
     assert L.magnet_gaussian_update_fwd_f32(None, p, 1, 4, p, None) == _lib.ERR_NULL
     with pytest.raises(_lib.MagnetError):
         _lib.check(_lib.ERR_SHAPE, "x")
@@ -69,7 +69,7 @@ def test_launch_info_matches_design():
     from magnet_b200 import ops
     grid, block, smem = ops.cost_launch_info(8, 4, 64, 64, 120, 160)
     assert (grid, block) == (8 * 150, 128)
-    assert smem == 8 * 3 * 128 * 16 + 8 * 128 * 8 + 64 * 128 * 4
+    assert smem == 5 * 3 * 128 * 16 + 5 * 128 * 8 + 32 * 128 * 4      # 5 records + 32-plane chunk
     grid, block, smem = ops.cost_launch_info(8, 4, 64, 64, 120, 160, variant=_lib.VARIANT_DIRECT)
     assert (grid, block, smem) == (150 * 64 * 8, 128, 0)
 
@@ -80,7 +80,7 @@ def test_ops_refuse_cpu_tensors():
     with pytest.raises(_lib.MagnetError):
         ops.gaussian_update(x, x)
     with pytest.raises(_lib.MagnetError):
-        ops.repack_c4hw4(torch.zeros(1, 4, 2, 2))
+        ops.repack_tiled32(torch.zeros(1, 4, 2, 2))
 
 
 def test_k_offsets():

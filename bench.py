@@ -345,7 +345,7 @@ def main():
     peak, peak_src = measured_peak()
     abytes = algorithmic_bytes(B, V, D, C, HW, fused=True)
     achieved = abytes / (kern_ms * 1e-3) / 1e9
-    grid, block, smem = ops.cost_launch_info(B, V, D, C, H, Wd, variant=variant)
+    grid, block, smem = ops.cost_launch_info(B, V, D, C, H, Wd, variant=_lib.VARIANT_CELLS if variant == _lib.VARIANT_CELLS_NOREUSE else variant)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(args.config), "kernel": "cost_cells_kernel<64,GAUSS,CW> (TILED32 gather)" if variant != _lib.VARIANT_DIRECT else "cost_direct_kernel<CW>",
                 "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src,

@@ -8,10 +8,10 @@
 namespace magnet {
 cudaError_t launch_cost_direct(const CostParams& p, int depth_mode, int src_layout, int C, bool cw,
                                bool softmax, cudaStream_t st, int* launches);
-cudaError_t launch_cost_cells(const CostParams& p, int mode, int C, bool cw, bool softmax, bool reuse,
-                              cudaStream_t st, int* launches);
-bool cells_supports(int C, int D, int layout, bool softmax);
-void cells_launch_info(int B, int H, int W, int D, bool softmax, int* grid, int* block, int* smem);
+cudaError_t launch_cost_cells(const CostParams& p, int mode, int C, bool cw, bool reuse, cudaStream_t st);
+cudaError_t launch_softmax_planes(float* vol, int B, int D, int HW, cudaStream_t st);
+bool cells_supports(int C, int D, int layout);
+void cells_launch_info(int B, int H, int W, int D, int* grid, int* block, int* smem);
 cudaError_t launch_pack_cameras(const float* intM, const float* R, int64_t r_sb, int64_t r_sv, int64_t r_si,
                                 int64_t r_sj, const float* t, int64_t t_sb, int64_t t_sv, int64_t t_si,
                                 const int32_t* is_valid, int B, int V, magnet_camera* out, cudaStream_t st);
@@ -54,7 +54,7 @@ int validate_cost(const magnet_cost_args* a) {
   }
   if (a->variant < MAGNET_VARIANT_AUTO || a->variant > MAGNET_VARIANT_CELLS_NOREUSE) return MAGNET_ERR_UNSUPPORTED;
   if ((a->variant == MAGNET_VARIANT_CELLS || a->variant == MAGNET_VARIANT_CELLS_NOREUSE) &&
-      !magnet::cells_supports(a->C, a->D, a->src_layout, a->softmax != 0))
+      !magnet::cells_supports(a->C, a->D, a->src_layout))
     return MAGNET_ERR_UNSUPPORTED;
   if (a->variant == MAGNET_VARIANT_CELLS_NOREUSE && a->depth_mode != MAGNET_DEPTH_GAUSS) return MAGNET_ERR_UNSUPPORTED;
   return MAGNET_OK;
@@ -62,7 +62,7 @@ int validate_cost(const magnet_cost_args* a) {
 
 bool use_cells(const magnet_cost_args* a) {
   if (a->variant == MAGNET_VARIANT_DIRECT) return false;
-  return magnet::cells_supports(a->C, a->D, a->src_layout, a->softmax != 0);
+  return magnet::cells_supports(a->C, a->D, a->src_layout);
 }
 }  // namespace
 
@@ -91,7 +91,7 @@ int magnet_cost_launch_info(const magnet_cost_args* a, int* grid_ctas, int* bloc
   if (st != MAGNET_OK) return st;
   if (!grid_ctas || !block_threads || !smem_bytes) return MAGNET_ERR_NULL;
   if (use_cells(a)) {
-    magnet::cells_launch_info(a->B, a->H, a->W, a->D, a->softmax != 0, grid_ctas, block_threads, smem_bytes);
+    magnet::cells_launch_info(a->B, a->H, a->W, a->D, grid_ctas, block_threads, smem_bytes);
   } else {
     *grid_ctas = ((a->H * a->W + 127) / 128) * a->D * a->B;
     *block_threads = 128;
@@ -112,14 +112,23 @@ int magnet_cost_volume_f32(const magnet_cost_args* a, void* stream) {
   p.cams = a->cams; p.d_volume = a->d_volume; p.ref_gmm = a->ref_gmm; p.out = a->out;
   for (int j = 0; j < MAGNET_MAX_PLANES; ++j)
     p.k[j] = (a->depth_mode != MAGNET_DEPTH_VOLUME && j < a->D) ? a->k_host[j] : 0.0f;
+  p.k_sorted = 1;
+  for (int j = 1; j < a->D; ++j)
+    if (!(p.k[j] >= p.k[j - 1])) p.k_sorted = 0;
   int launches = 0;
   cudaError_t e;
-  if (use_cells(a))
-    e = magnet::launch_cost_cells(p, a->depth_mode, a->C, a->consistency != 0, a->softmax != 0,
-                                  a->variant != MAGNET_VARIANT_CELLS_NOREUSE, (cudaStream_t)stream, &launches);
-  else
+  if (use_cells(a)) {
+    e = magnet::launch_cost_cells(p, a->depth_mode, a->C, a->consistency != 0,
+                                  a->variant != MAGNET_VARIANT_CELLS_NOREUSE, (cudaStream_t)stream);
+    launches = 1;
+    if (e == cudaSuccess && a->softmax) {          // homography.py:46, in place on the 1/V-averaged scores
+      e = magnet::launch_softmax_planes(a->out, a->B, a->D, a->H * a->W, (cudaStream_t)stream);
+      launches = 2;
+    }
+  } else {
     e = magnet::launch_cost_direct(p, a->depth_mode, a->src_layout, a->C, a->consistency != 0, a->softmax != 0,
                                    (cudaStream_t)stream, &launches);
+  }
   if (e != cudaSuccess) return cuda_fail(e);
   g_launches += launches;
   return MAGNET_OK;

@@ -10,6 +10,7 @@ namespace magnet {
 // (constant bank, uniform loads) so that no __constant__ symbol / extra copy is needed.
 struct CostParams {
   int B, V, D, H, W, HW;
+  int k_sorted;       // 1 when k[0..D) is non-decreasing (enables the analytic cell walk)
   float kappa;
   float inv_v_exact;  // 1/V when V is a power of two (exact), else 0 -> use IEEE division
   float vf;           // float(V)

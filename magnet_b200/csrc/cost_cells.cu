@@ -61,10 +61,11 @@ constexpr int TILE_H = NT / TILE_W;    // source footprint of a CTA compact enou
 constexpr int NCELL = MAGNET_NCELL;    // cell records per lane per round
 constexpr int JCHUNK = MAGNET_JCHUNK;  // hypotheses per accumulation chunk (non-softmax variants)
 
-__host__ __device__ inline int cells_chunk(int D, bool softmax) { return softmax ? D : (D < JCHUNK ? D : JCHUNK); }
-// dynamic shared memory: rec[NCELL][3][NT] float4 | hdr[NCELL][NT] float2 | acc[chunk][NT] float
-__host__ __device__ inline size_t cells_smem_bytes(int D, bool softmax) {
-  return (size_t)NCELL * 3 * NT * 16 + (size_t)NCELL * NT * 8 + (size_t)cells_chunk(D, softmax) * NT * 4;
+__host__ __device__ inline int cells_chunk(int D) { return D < JCHUNK ? D : JCHUNK; }
+// dynamic shared memory: rec[NCELL][3][NT] float4 | hdr[NCELL][NT] float4 | acc[chunk][NT] float | ks[chunk]
+__host__ __device__ inline size_t cells_smem_bytes(int D) {
+  return (size_t)NCELL * 3 * NT * 16 + (size_t)NCELL * NT * 16 + (size_t)cells_chunk(D) * NT * 4 +
+         (size_t)cells_chunk(D) * 4;
 }
 
 template <int MODE>
@@ -74,25 +75,28 @@ struct DepthSrc {
   int HW;
 };
 
-// Projection of hypothesis j: continuous source-image sample position (ix, iy) = projected
-// pixel - 0.5, and z = depth in the source camera.  Used by phases A and C;
-// written with explicit intrinsics so both phases get bit-identical results.
 template <int MODE>
-__device__ __forceinline__ void project(const CostParams& p, const DepthSrc<MODE>& ds, int j,
-                                        float a0, float a1, float a2, float q0, float q1, float q2,
-                                        float xmax, float ymax, float& ix, float& iy, float& z) {
-  float d;
-  if (MODE == MAGNET_DEPTH_VOLUME) d = ldg_f(ds.dv + (size_t)j * ds.HW);
-  else if (MODE == MAGNET_DEPTH_GAUSS) d = __fadd_rn(ds.mu, __fmul_rn(ds.sg, p.k[j]));
-  else d = p.k[j];
+__device__ __forceinline__ float depth_of(const CostParams& p, const DepthSrc<MODE>& ds, int j) {
+  if (MODE == MAGNET_DEPTH_VOLUME) return ldg_f(ds.dv + (size_t)j * ds.HW);
+  if (MODE == MAGNET_DEPTH_GAUSS) return __fadd_rn(ds.mu, __fmul_rn(ds.sg, p.k[j]));   // MAGNET.py:155: mul, then add
+  return p.k[j];
+}
+
+// Projection at depth d: continuous source-image sample position (ix, iy) = projected pixel - 0.5
+//  and z = depth in the source camera (exactly the reference's mul-then-add).
+__device__ __forceinline__ void project(float d, float a0, float a1, float a2, float q0, float q1, float q2,
+                                        float& ix, float& iy, float& z) {
   const float P0 = __fmaf_rn(q0, d, a0);
   const float P1 = __fmaf_rn(q1, d, a1);
-  z = __fadd_rn(a2, __fmul_rn(q2, d));            // exactly the reference's z (mul, then add)
+  z = __fadd_rn(a2, __fmul_rn(q2, d));
   const float r = rcp_nr(__fadd_rn(z, 1e-10f));
   ix = __fmaf_rn(P0, r, -0.5f);
   iy = __fmaf_rn(P1, r, -0.5f);
-  // Anything left of -1 / right of W (above / below likewise) has all four taps out of bounds;
-  // clamp so that cell coordinates stay small and NaN (fmaxf drops it) maps to "out of bounds".
+}
+
+// Anything left of -1 / right of W (above / below likewise) has all four taps out of bounds: clamp so
+// that cell coordinates stay small and NaN (fmaxf drops it) maps to "out of bounds" (exact walk only).
+__device__ __forceinline__ void clamp_pos(float& ix, float& iy, float xmax, float ymax) {
   ix = fminf(fmaxf(ix, -2.0f), xmax);
   iy = fminf(fmaxf(iy, -2.0f), ymax);
 }
@@ -134,21 +138,40 @@ __device__ __forceinline__ float4 bilinear_poly(float v00, float v01, float v10,
   return make_float4(v00, v01 - v00, v10 - v00, (v00 - v01) - (v10 - v11));
 }
 
-template <int C, int MODE, bool CW, bool SOFTMAX, bool REUSE>
+// Depth at which the projected sample crosses the vertical grid line ix == m (horizontal: swap the
+// roles of (a0,q0) and (a1,q1)):  (a0 + q0 d) / (a2 + q2 d) - 0.5 = m  =>  d = (c a2 - a0) / (q0 - c q2).
+__device__ __forceinline__ float crossing_depth(float m, float a_num, float q_num, float a2, float q2) {
+  const float c = m + 0.5f;
+  const float num = __fmaf_rn(c, a2, -a_num);
+  const float den = __fmaf_rn(-c, q2, q_num);
+  return den != 0.0f ? num * rcp_nr(den) : INFINITY;
+}
+
+// Cell-list header: cell origin (as floats) and the index of the first hypothesis of the NEXT cell.
+__device__ __forceinline__ float4 make_hdr(float cx, float cy, int jnext) {
+  return make_float4(cx, cy, __int_as_float(jnext), 0.0f);
+}
+
+template <int C, int MODE, bool CW, bool REUSE>
 __global__ void __launch_bounds__(NT, 4)
-cost_cells_kernel(const __grid_constant__ CostParams p) {
+cost_cells_kernel(const __grid_constant__ CostParams p, const int chunk) {
   extern __shared__ float4 smem4[];
   float4* rec = smem4;                                                   // [NCELL][3][NT]
-  float2* hdr = reinterpret_cast<float2*>(smem4 + NCELL * 3 * NT);       // [NCELL][NT]
+  float4* hdr = smem4 + NCELL * 3 * NT;                                  // [NCELL][NT]
   float* acc = reinterpret_cast<float*>(hdr + NCELL * NT);               // [chunk][NT]
+  float* ks = acc + chunk * NT;                                          // [chunk] k (or plane depth) table
 
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
   const int H = p.H, W = p.W, HW = p.HW, D = p.D;
   const int XB = (W + 31) >> 5;
   const int tiles_x = (W + TILE_W - 1) / TILE_W;
-  const int px = (blockIdx.x % tiles_x) * TILE_W + tid % TILE_W;
-  const int py = (blockIdx.x / tiles_x) * TILE_H + tid / TILE_W;
+  const int tiles = tiles_x * ((H + TILE_H - 1) / TILE_H);
+  const int tile = blockIdx.x % tiles;
+  const int jc = (blockIdx.x / tiles) * chunk;                           // hypothesis chunk of this CTA
+  const int jc_end = min(jc + chunk, D);
+  const int px = (tile % tiles_x) * TILE_W + tid % TILE_W;
+  const int py = (tile / tiles_x) * TILE_H + tid / TILE_W;
   const bool live = px < W && py < H;
   const int n = live ? py * W + px : HW - 1;    // dead lanes shadow the last pixel, never store
   const unsigned FULL = 0xffffffffu;
@@ -173,158 +196,205 @@ cost_cells_kernel(const __grid_constant__ CostParams p) {
     ds.sg = ldg_f(p.ref_gmm + ((size_t)b * 2 + 1) * HW + n);
   }
   const float xmax = (float)W + 1.0f, ymax = (float)H + 1.0f;
-  const int chunk = cells_chunk(D, SOFTMAX);
   const size_t img_stride4 = (size_t)H * XB * (C / 4) * 32;             // float4 per source image
 
-  for (int jc = 0; jc < D; jc += chunk) {
-    const int jc_end = min(jc + chunk, D);
-    for (int j = 0; j < jc_end - jc; ++j) acc[j * NT + tid] = 0.0f;
+  for (int j = 0; j < jc_end - jc; ++j) acc[j * NT + tid] = 0.0f;
+  if (MODE != MAGNET_DEPTH_VOLUME) {
+    for (int j = tid; j < jc_end - jc; j += NT) ks[j] = p.k[jc + j];
+    __syncthreads();
+  }
+  // The analytic walk needs depths that increase with j (sorted k, sigma > 0).
+  const bool lane_sorted = MODE == MAGNET_DEPTH_PLANES ? true : (ds.sg > 0.0f && ds.sg < 1e30f && fabsf(ds.mu) < 1e30f);
+  const bool can_walk = MODE != MAGNET_DEPTH_VOLUME && p.k_sorted != 0;
 
-    for (int v = 0; v < p.V; ++v) {
-      const magnet_camera* cam = p.cams + (b * p.V + v);
-      if (cam->valid != 1.0f) continue;                                  // CTA-uniform
-      const float a0 = cam->a[0], a1 = cam->a[1], a2 = cam->a[2];
-      const float q0 = __fmaf_rn(cam->A[2], r2, __fmaf_rn(cam->A[1], r1, __fmul_rn(cam->A[0], r0)));
-      const float q1 = __fmaf_rn(cam->A[5], r2, __fmaf_rn(cam->A[4], r1, __fmul_rn(cam->A[3], r0)));
-      const float q2 = __fmaf_rn(cam->A[8], r2, __fmaf_rn(cam->A[7], r1, __fmul_rn(cam->A[6], r0)));
-      const int vb = v * p.B + b;
-      const float4* src_img = reinterpret_cast<const float4*>(p.src_feat) + (size_t)vb * img_stride4;
-      const float* gm = CW ? p.src_gmm + (size_t)vb * 2 * HW : nullptr;
+  for (int v = 0; v < p.V; ++v) {
+    const magnet_camera* cam = p.cams + (b * p.V + v);
+    if (cam->valid != 1.0f) continue;                                    // CTA-uniform
+    const float a0 = cam->a[0], a1 = cam->a[1], a2 = cam->a[2];
+    const float q0 = __fmaf_rn(cam->A[2], r2, __fmaf_rn(cam->A[1], r1, __fmul_rn(cam->A[0], r0)));
+    const float q1 = __fmaf_rn(cam->A[5], r2, __fmaf_rn(cam->A[4], r1, __fmul_rn(cam->A[3], r0)));
+    const float q2 = __fmaf_rn(cam->A[8], r2, __fmaf_rn(cam->A[7], r1, __fmul_rn(cam->A[6], r0)));
+    const int vb = v * p.B + b;
+    const float4* src_img = reinterpret_cast<const float4*>(p.src_feat) + (size_t)vb * img_stride4;
+    const float* gm = CW ? p.src_gmm + (size_t)vb * 2 * HW : nullptr;
 
-      // previous cell of this lane (taps kept in registers for reuse by an edge-adjacent next cell)
-      int px0 = -1000000, py0 = -1000000;
-      Tap p00, p01, p10, p11;
-      p00.f = p00.m = p00.s = 0.f;
-      p01 = p10 = p11 = p00;
-
-      int j_lo = jc;
-      while (j_lo < jc_end) {                                            // rounds; warp-uniform
-        // ---------------- phase A: cell list ------------------------------------------------
-        int ncell = 0, j_stop = jc_end;
-        {
-          float cx = -1e30f, cy = -1e30f;
-          float2* hp = hdr + tid;
-#pragma unroll 2
-          for (int j = j_lo; j < jc_end; ++j) {
-            float ix, iy, z;
-            project<MODE>(p, ds, j, a0, a1, a2, q0, q1, q2, xmax, ymax, ix, iy, z);
-            const float fx = ix - cx, fy = iy - cy;
-            if (!(fx >= 0.0f && fx < 1.0f && fy >= 0.0f && fy < 1.0f)) {
-              if (ncell == NCELL) { j_stop = j; break; }
-              cx = floorf(ix);
-              cy = floorf(iy);
-              *hp = make_float2(cx, cy);
-              hp += NT;
-              ++ncell;
-            }
-          }
-        }
-        const int j_end = __reduce_min_sync(FULL, j_stop);
-        const int nmax = __reduce_max_sync(FULL, ncell);
-
-        // ---------------- phase B: per-cell records ------------------------------------------
-        for (int i = 0; i < nmax; ++i) {
-          if (i < ncell) {
-            const float2 h = hdr[i * NT + tid];
-            const int x0 = (int)h.x, y0 = (int)h.y;
-            const int dx = x0 - px0, dy = y0 - py0;
-            const bool mvx = REUSE && dy == 0 && (dx == 1 || dx == -1);
-            const bool mvy = REUSE && dx == 0 && (dy == 1 || dy == -1);
-            // two taps every lane computes: the new column (x move), the new row (y move), or the top row
-            int ax = x0, ay = y0, bx = x0 + 1, by = y0;
-            if (mvx) { ax = bx = (dx == 1) ? x0 + 1 : x0; by = y0 + 1; }
-            if (mvy) { ay = by = (dy == 1) ? y0 + 1 : y0; }
-            const Tap tA = load_tap<C, CW>(src_img, gm, ref2, ax, ay, W, H, XB, HW);
-            const Tap tB = load_tap<C, CW>(src_img, gm, ref2, bx, by, W, H, XB, HW);
-            Tap n00, n01, n10, n11;
-            if (mvx) {
-              if (dx == 1) { n00 = p01; n10 = p11; n01 = tA; n11 = tB; }
-              else         { n01 = p00; n11 = p10; n00 = tA; n10 = tB; }
-            } else if (mvy) {
-              if (dy == 1) { n00 = p10; n01 = p11; n10 = tA; n11 = tB; }
-              else         { n10 = p00; n11 = p01; n00 = tA; n01 = tB; }
-            } else {                                                     // first cell / diagonal / jump
-              n00 = tA; n01 = tB;
-              n10 = load_tap<C, CW>(src_img, gm, ref2, x0, y0 + 1, W, H, XB, HW);
-              n11 = load_tap<C, CW>(src_img, gm, ref2, x0 + 1, y0 + 1, W, H, XB, HW);
-            }
-            p00 = n00; p01 = n01; p10 = n10; p11 = n11;
-            px0 = x0; py0 = y0;
-            rec[(i * 3 + 0) * NT + tid] = bilinear_poly(n00.f, n01.f, n10.f, n11.f);
-            if (CW) {
-              rec[(i * 3 + 1) * NT + tid] = bilinear_poly(n00.m, n01.m, n10.m, n11.m);
-              rec[(i * 3 + 2) * NT + tid] = bilinear_poly(n00.s, n01.s, n10.s, n11.s);
-            }
-          }
-        }
-
-        // ---------------- phase C: evaluate hypotheses [j_lo, j_end) -------------------------
-        {
-          float cx = -1e30f, cy = -1e30f;
-          float4 rd = make_float4(0.f, 0.f, 0.f, 0.f), rm = rd, rs = rd;
-          const float2* hp = hdr + tid - NT;
-          const float4* rp = rec + tid - 3 * NT;
-          float* ap = acc + (j_lo - jc) * NT + tid;
-#pragma unroll 2
-          for (int j = j_lo; j < j_end; ++j, ap += NT) {
-            float ix, iy, z;
-            project<MODE>(p, ds, j, a0, a1, a2, q0, q1, q2, xmax, ymax, ix, iy, z);
-            float fx = ix - cx, fy = iy - cy;
-            if (!(fx >= 0.0f && fx < 1.0f && fy >= 0.0f && fy < 1.0f)) {
-              hp += NT;
-              rp += 3 * NT;
-              const float2 h = *hp;
-              cx = h.x;
-              cy = h.y;
-              rd = rp[0];
-              if (CW) {
-                rm = rp[NT];
-                rs = rp[2 * NT];
-              }
-              fx = ix - cx;
-              fy = iy - cy;
-            }
-            const float cost = __fmaf_rn(fy, __fmaf_rn(fx, rd.w, rd.z), __fmaf_rn(fx, rd.y, rd.x));
-            float val = cost;
-            if (CW) {
-              const float mu = __fmaf_rn(fy, __fmaf_rn(fx, rm.w, rm.z), __fmaf_rn(fx, rm.y, rm.x));
-              const float sg = __fmaf_rn(fy, __fmaf_rn(fx, rs.w, rs.z), __fmaf_rn(fx, rs.y, rs.x));
-              // homography.py:157-158: |z - mu~| < sigma~ * kappa, strict
-              val = (fabsf(__fsub_rn(z, mu)) < __fmul_rn(sg, p.kappa)) ? cost : 0.0f;
-            }
-            *ap += val;
-          }
-        }
-        j_lo = j_end;
-      }
+    // Analytic walk is valid when every hypothesis of the chunk is in front of the source camera:
+    // z is linear in depth, so checking both ends suffices; ix(d), iy(d) are then monotone.
+    bool walk = false;
+    if (can_walk) {
+      const float zA = __fadd_rn(a2, __fmul_rn(q2, depth_of<MODE>(p, ds, jc)));
+      const float zB = __fadd_rn(a2, __fmul_rn(q2, depth_of<MODE>(p, ds, jc_end - 1)));
+      const bool ok = lane_sorted && zA > 1e-6f && zB > 1e-6f && zA < 1e30f && zB < 1e30f;
+      walk = __all_sync(FULL, ok);                                       // warp-uniform choice
     }
+    // direction of travel of the sample as depth grows: sign of d(ix)/dd = (q0 a2 - a0 q2) / z^2
+    const float gx = __fmaf_rn(q0, a2, -__fmul_rn(a0, q2)), gy = __fmaf_rn(q1, a2, -__fmul_rn(a1, q2));
+    const int sx = gx > 0.0f ? 1 : (gx < 0.0f ? -1 : 0), sy = gy > 0.0f ? 1 : (gy < 0.0f ? -1 : 0);
 
-    // -------- chunk epilogue: 1/V mean over ALL views (homography.py:120), optional softmax ------
+    // previous cell of this lane (taps kept in registers for reuse by an edge-adjacent next cell)
+    int px0 = -1000000, py0 = -1000000;
+    Tap p00, p01, p10, p11;
+    p00.f = p00.m = p00.s = 0.f;
+    p01 = p10 = p11 = p00;
+
+    int j_lo = jc;
+    while (j_lo < jc_end) {                                              // rounds; warp-uniform
+      // ---------------- phase A: cell list ----------------------------------------------------
+      int ncell = 0, j_stop = jc_end;
+      if (walk) {
+        // A-walk: step from grid line to grid line in depth space (the sample path is a straight line,
+        // monotone in depth); the first hypothesis of the next cell is found by binary search in the
+        // sorted k table.  The bilinear interpolant is continuous across cell edges, so a hypothesis that
+        // rounding puts on the "wrong" side of an edge changes the result by O(1e-6).
+        float ix, iy, z;
+        project(depth_of<MODE>(p, ds, j_lo), a0, a1, a2, q0, q1, q2, ix, iy, z);
+        clamp_pos(ix, iy, xmax, ymax);
+        int x0 = min((int)floorf(ix), W), y0 = min((int)floorf(iy), H);          // in [-2, W] x [-2, H]
+        // next grid line in the direction of travel; lines exist only at -1..W (x) / -1..H (y)
+        int mx = sx > 0 ? x0 + 1 : x0, my = sy > 0 ? y0 + 1 : y0;
+        float dX = (sx != 0 && mx >= -1 && mx <= W) ? crossing_depth((float)mx, a0, q0, a2, q2) : INFINITY;
+        float dY = (sy != 0 && my >= -1 && my <= H) ? crossing_depth((float)my, a1, q1, a2, q2) : INFINITY;
+        const float inv_sg = MODE == MAGNET_DEPTH_GAUSS ? rcp_nr(ds.sg) : 1.0f;
+        int jcur = j_lo;
+        bool done = false;
+        while (__any_sync(FULL, !done)) {
+          if (!done) {
+            const float dn = fminf(dX, dY);
+            // first j in [jcur, jc_end) with depth_j >= dn  <=>  k_j >= kc
+            const float kc = MODE == MAGNET_DEPTH_GAUSS ? (dn - ds.mu) * inv_sg : dn;
+            int lo = jcur, hi = jc_end;
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (ks[mid - jc] < kc) lo = mid + 1; else hi = mid;
+            }
+            if (lo > jcur) {                                             // the cell holds hypotheses
+              hdr[ncell * NT + tid] = make_hdr((float)x0, (float)y0, lo);
+              ++ncell;
+              jcur = lo;
+            }
+            if (jcur >= jc_end) {
+              done = true;
+            } else if (ncell == NCELL) {
+              j_stop = jcur;
+              done = true;
+            } else if (dX <= dY) {
+              x0 += sx;
+              mx += sx;
+              dX = (mx >= -1 && mx <= W) ? crossing_depth((float)mx, a0, q0, a2, q2) : INFINITY;
+            } else {
+              y0 += sy;
+              my += sy;
+              dY = (my >= -1 && my <= H) ? crossing_depth((float)my, a1, q1, a2, q2) : INFINITY;
+            }
+          }
+        }
+      } else {
+        // A-exact: evaluate every hypothesis, record each change of cell (any depth order, any sign of z).
+        float cx = -1e30f, cy = -1e30f;
+        for (int j = j_lo; j < jc_end; ++j) {
+          float ix, iy, z;
+          project(depth_of<MODE>(p, ds, j), a0, a1, a2, q0, q1, q2, ix, iy, z);
+          clamp_pos(ix, iy, xmax, ymax);
+          const float fx = ix - cx, fy = iy - cy;
+          if (!(fx >= 0.0f && fx < 1.0f && fy >= 0.0f && fy < 1.0f)) {
+            if (ncell > 0) hdr[(ncell - 1) * NT + tid].z = __int_as_float(j);   // previous cell ends here
+            if (ncell == NCELL) { j_stop = j; break; }
+            cx = floorf(ix);
+            cy = floorf(iy);
+            hdr[ncell * NT + tid] = make_hdr(cx, cy, jc_end);
+            ++ncell;
+          }
+        }
+      }
+      const int j_end = __reduce_min_sync(FULL, j_stop);
+      const int nmax = __reduce_max_sync(FULL, ncell);
+
+      // ---------------- phase B: per-cell records ----------------------------------------------
+      for (int i = 0; i < nmax; ++i) {
+        if (i < ncell) {
+          const float4 h = hdr[i * NT + tid];
+          const int x0 = (int)h.x, y0 = (int)h.y;
+          const int dx = x0 - px0, dy = y0 - py0;
+          const bool mvx = REUSE && dy == 0 && (dx == 1 || dx == -1);
+          const bool mvy = REUSE && dx == 0 && (dy == 1 || dy == -1);
+          // two taps every lane computes: the new column (x move), the new row (y move), or the top row
+          int ax = x0, ay = y0, bx = x0 + 1, by = y0;
+          if (mvx) { ax = bx = (dx == 1) ? x0 + 1 : x0; by = y0 + 1; }
+          if (mvy) { ay = by = (dy == 1) ? y0 + 1 : y0; }
+          const Tap tA = load_tap<C, CW>(src_img, gm, ref2, ax, ay, W, H, XB, HW);
+          const Tap tB = load_tap<C, CW>(src_img, gm, ref2, bx, by, W, H, XB, HW);
+          Tap n00, n01, n10, n11;
+          if (mvx) {
+            if (dx == 1) { n00 = p01; n10 = p11; n01 = tA; n11 = tB; }
+            else         { n01 = p00; n11 = p10; n00 = tA; n10 = tB; }
+          } else if (mvy) {
+            if (dy == 1) { n00 = p10; n01 = p11; n10 = tA; n11 = tB; }
+            else         { n10 = p00; n11 = p01; n00 = tA; n01 = tB; }
+          } else {                                                       // first cell / diagonal / jump
+            n00 = tA; n01 = tB;
+            n10 = load_tap<C, CW>(src_img, gm, ref2, x0, y0 + 1, W, H, XB, HW);
+            n11 = load_tap<C, CW>(src_img, gm, ref2, x0 + 1, y0 + 1, W, H, XB, HW);
+          }
+          p00 = n00; p01 = n01; p10 = n10; p11 = n11;
+          px0 = x0; py0 = y0;
+          rec[(i * 3 + 0) * NT + tid] = bilinear_poly(n00.f, n01.f, n10.f, n11.f);
+          if (CW) {
+            rec[(i * 3 + 1) * NT + tid] = bilinear_poly(n00.m, n01.m, n10.m, n11.m);
+            rec[(i * 3 + 2) * NT + tid] = bilinear_poly(n00.s, n01.s, n10.s, n11.s);
+          }
+        }
+      }
+
+      // ---------------- phase C: evaluate hypotheses [j_lo, j_end) -----------------------------
+      {
+        float cx = 0.0f, cy = 0.0f;
+        int jnext = j_lo;                                                // forces the load of record 0
+        float4 rd = make_float4(0.f, 0.f, 0.f, 0.f), rm = rd, rs = rd;
+        const float4* hp = hdr + tid - NT;
+        const float4* rp = rec + tid - 3 * NT;
+        float* ap = acc + (j_lo - jc) * NT + tid;
+#pragma unroll 4
+        for (int j = j_lo; j < j_end; ++j, ap += NT) {
+          float ix, iy, z;
+          project(depth_of<MODE>(p, ds, j), a0, a1, a2, q0, q1, q2, ix, iy, z);
+          if (j == jnext) {                                              // entering the lane's next cell
+            hp += NT;
+            rp += 3 * NT;
+            const float4 h = *hp;
+            cx = h.x;
+            cy = h.y;
+            jnext = __float_as_int(h.z);
+            rd = rp[0];
+            if (CW) {
+              rm = rp[NT];
+              rs = rp[2 * NT];
+            }
+          }
+          const float fx = ix - cx, fy = iy - cy;
+          float cost = __fmaf_rn(fy, __fmaf_rn(fx, rd.w, rd.z), __fmaf_rn(fx, rd.y, rd.x));
+          if (!(fabsf(cost) < 3.0e38f)) cost = 0.0f;                     // all-zero record x non-finite position
+          float val = cost;
+          if (CW) {
+            const float mu = __fmaf_rn(fy, __fmaf_rn(fx, rm.w, rm.z), __fmaf_rn(fx, rm.y, rm.x));
+            const float sg = __fmaf_rn(fy, __fmaf_rn(fx, rs.w, rs.z), __fmaf_rn(fx, rs.y, rs.x));
+            // homography.py:157-158: |z - mu~| < sigma~ * kappa, strict
+            val = (fabsf(__fsub_rn(z, mu)) < __fmul_rn(sg, p.kappa)) ? cost : 0.0f;
+          }
+          *ap += val;
+        }
+      }
+      j_lo = j_end;
+    }
+  }
+
+  // -------- epilogue: 1/V mean over ALL views (homography.py:120) ---------------------------------
+  if (live) {
     float* outp = p.out + ((size_t)b * D + jc) * HW + n;
     const int cnt = jc_end - jc;
-    if (!SOFTMAX) {
-      if (live) {
-        if (p.inv_v_exact != 0.0f) {
-          for (int j = 0; j < cnt; ++j) outp[(size_t)j * HW] = acc[j * NT + tid] * p.inv_v_exact;
-        } else {
-          for (int j = 0; j < cnt; ++j) outp[(size_t)j * HW] = __fdiv_rn(acc[j * NT + tid], p.vf);
-        }
-      }
-    } else {                                                             // chunk == D here
-      float m = -INFINITY;
-      for (int j = 0; j < cnt; ++j) {
-        const float x = __fdiv_rn(acc[j * NT + tid], p.vf);
-        acc[j * NT + tid] = x;
-        m = fmaxf(m, x);
-      }
-      float s = 0.0f;
-      for (int j = 0; j < cnt; ++j) {
-        const float e = expf(acc[j * NT + tid] - m);
-        acc[j * NT + tid] = e;
-        s += e;
-      }
-      if (live)
-        for (int j = 0; j < cnt; ++j) outp[(size_t)j * HW] = __fdiv_rn(acc[j * NT + tid], s);
+    if (p.inv_v_exact != 0.0f) {
+      for (int j = 0; j < cnt; ++j) outp[(size_t)j * HW] = acc[j * NT + tid] * p.inv_v_exact;
+    } else {
+      for (int j = 0; j < cnt; ++j) outp[(size_t)j * HW] = __fdiv_rn(acc[j * NT + tid], p.vf);
     }
   }
 }
@@ -344,58 +414,55 @@ static int cells_carveout_pct(size_t smem_per_cta) {
 }
 
 template <int C, int MODE, bool REUSE>
-static cudaError_t launch_cm(const CostParams& p, bool cw, bool softmax, cudaStream_t st) {
-  const size_t smem = cells_smem_bytes(p.D, softmax);
-  dim3 grid(cells_grid_x(p.H, p.W), p.B), block(NT);
+static cudaError_t launch_cm(const CostParams& p, bool cw, cudaStream_t st) {
+  const size_t smem = cells_smem_bytes(p.D);
+  const int chunk = cells_chunk(p.D), nchunks = (p.D + chunk - 1) / chunk;
+  dim3 grid(cells_grid_x(p.H, p.W) * nchunks, p.B), block(NT);
   const int carve = cells_carveout_pct(smem);
-#define MAGNET_LAUNCH(CWv, SMv)                                                                         \
+#define MAGNET_LAUNCH(CWv)                                                                              \
   do {                                                                                                  \
-    auto kern = cost_cells_kernel<C, MODE, CWv, SMv, REUSE>;                                            \
+    auto kern = cost_cells_kernel<C, MODE, CWv, REUSE>;                                                 \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                     \
     if (carve > 0) {                                                                                    \
       e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);            \
       if (e != cudaSuccess) return e;                                                                   \
     }                                                                                                   \
-    kern<<<grid, block, smem, st>>>(p);                                                                 \
+    kern<<<grid, block, smem, st>>>(p, chunk);                                                          \
     return cudaGetLastError();                                                                          \
   } while (0)
-  if (cw && !softmax) MAGNET_LAUNCH(true, false);
-  if (!cw && softmax) MAGNET_LAUNCH(false, true);
-  if (!cw && !softmax) MAGNET_LAUNCH(false, false);
+  if (cw) MAGNET_LAUNCH(true);
+  MAGNET_LAUNCH(false);
 #undef MAGNET_LAUNCH
-  return cudaErrorInvalidValue;   // cw && softmax is not a reference configuration
 }
 
 template <int C>
-static cudaError_t launch_c(const CostParams& p, int mode, bool cw, bool softmax, bool reuse, cudaStream_t st) {
+static cudaError_t launch_c(const CostParams& p, int mode, bool cw, bool reuse, cudaStream_t st) {
   if (!reuse) {   // diagnostic variant: only the bench configuration is instantiated
-    if (mode == MAGNET_DEPTH_GAUSS) return launch_cm<C, MAGNET_DEPTH_GAUSS, false>(p, cw, softmax, st);
+    if (mode == MAGNET_DEPTH_GAUSS) return launch_cm<C, MAGNET_DEPTH_GAUSS, false>(p, cw, st);
     return cudaErrorInvalidValue;
   }
-  if (mode == MAGNET_DEPTH_VOLUME) return launch_cm<C, MAGNET_DEPTH_VOLUME, true>(p, cw, softmax, st);
-  if (mode == MAGNET_DEPTH_GAUSS) return launch_cm<C, MAGNET_DEPTH_GAUSS, true>(p, cw, softmax, st);
-  return launch_cm<C, MAGNET_DEPTH_PLANES, true>(p, cw, softmax, st);
+  if (mode == MAGNET_DEPTH_VOLUME) return launch_cm<C, MAGNET_DEPTH_VOLUME, true>(p, cw, st);
+  if (mode == MAGNET_DEPTH_GAUSS) return launch_cm<C, MAGNET_DEPTH_GAUSS, true>(p, cw, st);
+  return launch_cm<C, MAGNET_DEPTH_PLANES, true>(p, cw, st);
 }
 
-bool cells_supports(int C, int D, int layout, bool softmax) {
-  return (C == 16 || C == 32 || C == 64) && layout == MAGNET_SRC_TILED32 &&
-         cells_smem_bytes(D, softmax) <= 200 * 1024;
+bool cells_supports(int C, int D, int layout) {
+  return (C == 16 || C == 32 || C == 64) && layout == MAGNET_SRC_TILED32 && D >= 1;
 }
 
-void cells_launch_info(int B, int H, int W, int D, bool softmax, int* grid, int* block, int* smem) {
-  *grid = cells_grid_x(H, W) * B;
+void cells_launch_info(int B, int H, int W, int D, int* grid, int* block, int* smem) {
+  const int chunk = cells_chunk(D);
+  *grid = cells_grid_x(H, W) * ((D + chunk - 1) / chunk) * B;
   *block = NT;
-  *smem = (int)cells_smem_bytes(D, softmax);
+  *smem = (int)cells_smem_bytes(D);
 }
 
-cudaError_t launch_cost_cells(const CostParams& p, int mode, int C, bool cw, bool softmax, bool reuse,
-                              cudaStream_t st, int* launches) {
-  *launches = 1;
+cudaError_t launch_cost_cells(const CostParams& p, int mode, int C, bool cw, bool reuse, cudaStream_t st) {
   switch (C) {
-    case 16: return launch_c<16>(p, mode, cw, softmax, reuse, st);
-    case 32: return launch_c<32>(p, mode, cw, softmax, reuse, st);
-    case 64: return launch_c<64>(p, mode, cw, softmax, reuse, st);
+    case 16: return launch_c<16>(p, mode, cw, reuse, st);
+    case 32: return launch_c<32>(p, mode, cw, reuse, st);
+    case 64: return launch_c<64>(p, mode, cw, reuse, st);
     default: return cudaErrorInvalidValue;
   }
 }

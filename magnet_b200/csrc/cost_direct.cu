@@ -138,6 +138,11 @@ __global__ void softmax_planes_kernel(float* __restrict__ vol, int D, int HW) {
   for (int j = 0; j < D; ++j) col[(size_t)j * HW] = __fdiv_rn(expf(col[(size_t)j * HW] - m), s);
 }
 
+cudaError_t launch_softmax_planes(float* vol, int B, int D, int HW, cudaStream_t st) {
+  softmax_planes_kernel<<<dim3((HW + 127) / 128, B), 128, 0, st>>>(vol, D, HW);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_cost_direct(const CostParams& p, int depth_mode, int src_layout, int C, bool cw,
                                bool softmax, cudaStream_t st, int* launches) {
   dim3 grid((p.HW + 127) / 128, p.D, p.B), block(128);

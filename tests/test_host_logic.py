@@ -68,8 +68,8 @@ def test_cost_args_validation_without_gpu():
 def test_launch_info_matches_design():
     from magnet_b200 import ops
     grid, block, smem = ops.cost_launch_info(8, 4, 64, 64, 120, 160)
-    assert (grid, block) == (8 * 10 * 15, 128)                          # 16 x 8 pixel tiles
-    assert smem == 4 * 3 * 128 * 16 + 4 * 128 * 8 + 32 * 128 * 4      # 4 records + 32-plane chunk
+    assert (grid, block) == (8 * 10 * 15 * 2, 128)                      # 16 x 8 pixel tiles x 2 chunks of 32 planes
+    assert smem == 4 * 3 * 128 * 16 + 4 * 128 * 16 + 32 * 128 * 4 + 32 * 4   # 4 records + headers + chunk + k
     grid, block, smem = ops.cost_launch_info(8, 4, 64, 64, 120, 160, variant=_lib.VARIANT_DIRECT)
     assert (grid, block, smem) == (150 * 64 * 8, 128, 0)
 

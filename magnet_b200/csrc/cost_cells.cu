@@ -140,11 +140,14 @@ __device__ __forceinline__ float4 bilinear_poly(float v00, float v01, float v10,
 
 // Depth at which the projected sample crosses the vertical grid line ix == m (horizontal: swap the
 // roles of (a0,q0) and (a1,q1)):  (a0 + q0 d) / (a2 + q2 d) - 0.5 = m  =>  d = (c a2 - a0) / (q0 - c q2).
-__device__ __forceinline__ float crossing_depth(float m, float a_num, float q_num, float a2, float q2) {
+// The position is a Moebius function of depth: a grid line beyond its asymptote is only "crossed" on the other
+// branch (behind the current depth) — such a line is never reached, so anything not ahead of `dcur` is +inf.
+__device__ __forceinline__ float crossing_depth(float m, float a_num, float q_num, float a2, float q2, float dcur) {
   const float c = m + 0.5f;
   const float num = __fmaf_rn(c, a2, -a_num);
   const float den = __fmaf_rn(-c, q2, q_num);
-  return den != 0.0f ? num * rcp_nr(den) : INFINITY;
+  const float d = den != 0.0f ? num * rcp_nr(den) : INFINITY;
+  return d >= __fmaf_rn(-1e-5f, fabsf(dcur), dcur) - 1e-12f ? d : INFINITY;
 }
 
 // Cell-list header: cell origin (as floats) and the index of the first hypothesis of the NEXT cell.
@@ -247,13 +250,14 @@ cost_cells_kernel(const __grid_constant__ CostParams p, const int chunk) {
         // sorted k table.  The bilinear interpolant is continuous across cell edges, so a hypothesis that
         // rounding puts on the "wrong" side of an edge changes the result by O(1e-6).
         float ix, iy, z;
-        project(depth_of<MODE>(p, ds, j_lo), a0, a1, a2, q0, q1, q2, ix, iy, z);
+        const float d_lo = depth_of<MODE>(p, ds, j_lo);
+        project(d_lo, a0, a1, a2, q0, q1, q2, ix, iy, z);
         clamp_pos(ix, iy, xmax, ymax);
         int x0 = min((int)floorf(ix), W), y0 = min((int)floorf(iy), H);          // in [-2, W] x [-2, H]
         // next grid line in the direction of travel; lines exist only at -1..W (x) / -1..H (y)
         int mx = sx > 0 ? x0 + 1 : x0, my = sy > 0 ? y0 + 1 : y0;
-        float dX = (sx != 0 && mx >= -1 && mx <= W) ? crossing_depth((float)mx, a0, q0, a2, q2) : INFINITY;
-        float dY = (sy != 0 && my >= -1 && my <= H) ? crossing_depth((float)my, a1, q1, a2, q2) : INFINITY;
+        float dX = (sx != 0 && mx >= -1 && mx <= W) ? crossing_depth((float)mx, a0, q0, a2, q2, d_lo) : INFINITY;
+        float dY = (sy != 0 && my >= -1 && my <= H) ? crossing_depth((float)my, a1, q1, a2, q2, d_lo) : INFINITY;
         const float inv_sg = MODE == MAGNET_DEPTH_GAUSS ? rcp_nr(ds.sg) : 1.0f;
         int jcur = j_lo;
         bool done = false;
@@ -280,11 +284,11 @@ cost_cells_kernel(const __grid_constant__ CostParams p, const int chunk) {
             } else if (dX <= dY) {
               x0 += sx;
               mx += sx;
-              dX = (mx >= -1 && mx <= W) ? crossing_depth((float)mx, a0, q0, a2, q2) : INFINITY;
+              dX = (mx >= -1 && mx <= W) ? crossing_depth((float)mx, a0, q0, a2, q2, dX) : INFINITY;
             } else {
               y0 += sy;
               my += sy;
-              dY = (my >= -1 && my <= H) ? crossing_depth((float)my, a1, q1, a2, q2) : INFINITY;
+              dY = (my >= -1 && my <= H) ? crossing_depth((float)my, a1, q1, a2, q2, dY) : INFINITY;
             }
           }
         }

@@ -58,8 +58,10 @@ typedef enum magnet_variant {
   MAGNET_VARIANT_DIRECT = 1, /* one thread per output, 4 taps x C channels per hypothesis,
                                 reference operation order, fp64 view accumulation             */
   MAGNET_VARIANT_CELLS = 2,  /* tap-sharing kernel: per-lane bilinear-cell records             */
-  MAGNET_VARIANT_CELLS_NOREUSE = 3 /* diagnostic: as CELLS, but every cell gathers all 4 taps
-                                      (MAGNET_DEPTH_GAUSS only)                                */
+  MAGNET_VARIANT_CELLS_NOREUSE = 3, /* diagnostic: as CELLS, but every cell gathers all 4 taps
+                                       (MAGNET_DEPTH_GAUSS only)                               */
+  MAGNET_VARIANT_WINDOW = 4  /* tap-sharing kernel with the CTA's source window staged in shared
+                                memory (cp.async), accumulators in registers                   */
 } magnet_variant;
 
 /* Per (batch element, view) camera constants, 16 floats, produced by magnet_pack_cameras_f32.

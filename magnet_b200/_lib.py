@@ -21,7 +21,7 @@ MAGNET_MAX_PLANES = 256
 OK, ERR_NULL, ERR_SHAPE, ERR_UNSUPPORTED, ERR_CUDA, ERR_ALIGN = 0, -1, -2, -3, -4, -5
 DEPTH_VOLUME, DEPTH_GAUSS, DEPTH_PLANES = 0, 1, 2
 SRC_NCHW, SRC_TILED32 = 0, 1
-VARIANT_AUTO, VARIANT_DIRECT, VARIANT_CELLS, VARIANT_CELLS_NOREUSE = 0, 1, 2, 3
+VARIANT_AUTO, VARIANT_DIRECT, VARIANT_CELLS, VARIANT_CELLS_NOREUSE, VARIANT_WINDOW = 0, 1, 2, 3, 4
 
 # every symbol include/magnet_b200.h declares (tests check the library exports all of them)
 EXPORTS = (

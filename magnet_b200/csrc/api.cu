@@ -11,6 +11,9 @@ cudaError_t launch_cost_direct(const CostParams& p, int depth_mode, int src_layo
 cudaError_t launch_cost_cells(const CostParams& p, int mode, int C, bool cw, bool reuse, cudaStream_t st);
 cudaError_t launch_softmax_planes(float* vol, int B, int D, int HW, cudaStream_t st);
 bool cells_supports(int C, int D, int layout);
+cudaError_t launch_cost_window(const CostParams& p, int mode, int C, bool cw, cudaStream_t st);
+bool window_supports(int C, int D, int layout);
+void window_launch_info(int B, int H, int W, int D, int C, int* grid, int* block, int* smem);
 void cells_launch_info(int B, int H, int W, int D, int* grid, int* block, int* smem);
 cudaError_t launch_pack_cameras(const float* intM, const float* R, int64_t r_sb, int64_t r_sv, int64_t r_si,
                                 int64_t r_sj, const float* t, int64_t t_sb, int64_t t_sv, int64_t t_si,
@@ -52,7 +55,9 @@ int validate_cost(const magnet_cost_args* a) {
   } else if (a->src_layout != MAGNET_SRC_NCHW) {
     return MAGNET_ERR_UNSUPPORTED;
   }
-  if (a->variant < MAGNET_VARIANT_AUTO || a->variant > MAGNET_VARIANT_CELLS_NOREUSE) return MAGNET_ERR_UNSUPPORTED;
+  if (a->variant < MAGNET_VARIANT_AUTO || a->variant > MAGNET_VARIANT_WINDOW) return MAGNET_ERR_UNSUPPORTED;
+  if (a->variant == MAGNET_VARIANT_WINDOW && !magnet::window_supports(a->C, a->D, a->src_layout))
+    return MAGNET_ERR_UNSUPPORTED;
   if ((a->variant == MAGNET_VARIANT_CELLS || a->variant == MAGNET_VARIANT_CELLS_NOREUSE) &&
       !magnet::cells_supports(a->C, a->D, a->src_layout))
     return MAGNET_ERR_UNSUPPORTED;
@@ -61,8 +66,14 @@ int validate_cost(const magnet_cost_args* a) {
 }
 
 bool use_cells(const magnet_cost_args* a) {
-  if (a->variant == MAGNET_VARIANT_DIRECT) return false;
+  if (a->variant == MAGNET_VARIANT_DIRECT || a->variant == MAGNET_VARIANT_WINDOW) return false;
+  if (a->variant == MAGNET_VARIANT_AUTO) return false;     // AUTO prefers the window kernel, see use_window
   return magnet::cells_supports(a->C, a->D, a->src_layout);
+}
+
+bool use_window(const magnet_cost_args* a) {
+  if (a->variant != MAGNET_VARIANT_AUTO && a->variant != MAGNET_VARIANT_WINDOW) return false;
+  return magnet::window_supports(a->C, a->D, a->src_layout);
 }
 }  // namespace
 
@@ -90,7 +101,9 @@ int magnet_cost_launch_info(const magnet_cost_args* a, int* grid_ctas, int* bloc
   const int st = validate_cost(a);
   if (st != MAGNET_OK) return st;
   if (!grid_ctas || !block_threads || !smem_bytes) return MAGNET_ERR_NULL;
-  if (use_cells(a)) {
+  if (use_window(a)) {
+    magnet::window_launch_info(a->B, a->H, a->W, a->D, a->C, grid_ctas, block_threads, smem_bytes);
+  } else if (use_cells(a)) {
     magnet::cells_launch_info(a->B, a->H, a->W, a->D, grid_ctas, block_threads, smem_bytes);
   } else {
     *grid_ctas = ((a->H * a->W + 127) / 128) * a->D * a->B;
@@ -117,7 +130,10 @@ int magnet_cost_volume_f32(const magnet_cost_args* a, void* stream) {
     if (!(p.k[j] >= p.k[j - 1])) p.k_sorted = 0;
   int launches = 0;
   cudaError_t e;
-  if (use_cells(a)) {
+  if (use_window(a) || use_cells(a)) {
+    if (use_window(a))
+      e = magnet::launch_cost_window(p, a->depth_mode, a->C, a->consistency != 0, (cudaStream_t)stream);
+    else
     e = magnet::launch_cost_cells(p, a->depth_mode, a->C, a->consistency != 0,
                                   a->variant != MAGNET_VARIANT_CELLS_NOREUSE, (cudaStream_t)stream);
     launches = 1;

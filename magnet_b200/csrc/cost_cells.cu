@@ -39,7 +39,7 @@
 // within ~1e-5 of it (the reference's own fp32-vs-fp64 flips have the same margins).
 #include <cstdlib>
 
-#include "common.cuh"
+#include "cells_common.cuh"
 
 namespace magnet {
 
@@ -66,93 +66,6 @@ __host__ __device__ inline int cells_chunk(int D) { return D < JCHUNK ? D : JCHU
 __host__ __device__ inline size_t cells_smem_bytes(int D) {
   return (size_t)NCELL * 3 * NT * 16 + (size_t)NCELL * NT * 16 + (size_t)cells_chunk(D) * NT * 4 +
          (size_t)cells_chunk(D) * 4;
-}
-
-template <int MODE>
-struct DepthSrc {
-  float mu, sg;
-  const float* dv;   // d_volume + b*D*HW + n
-  int HW;
-};
-
-template <int MODE>
-__device__ __forceinline__ float depth_of(const CostParams& p, const DepthSrc<MODE>& ds, int j) {
-  if (MODE == MAGNET_DEPTH_VOLUME) return ldg_f(ds.dv + (size_t)j * ds.HW);
-  if (MODE == MAGNET_DEPTH_GAUSS) return __fadd_rn(ds.mu, __fmul_rn(ds.sg, p.k[j]));   // MAGNET.py:155: mul, then add
-  return p.k[j];
-}
-
-// Projection at depth d: continuous source-image sample position (ix, iy) = projected pixel - 0.5
-//  and z = depth in the source camera (exactly the reference's mul-then-add).
-__device__ __forceinline__ void project(float d, float a0, float a1, float a2, float q0, float q1, float q2,
-                                        float& ix, float& iy, float& z) {
-  const float P0 = __fmaf_rn(q0, d, a0);
-  const float P1 = __fmaf_rn(q1, d, a1);
-  z = __fadd_rn(a2, __fmul_rn(q2, d));
-  const float r = rcp_nr(__fadd_rn(z, 1e-10f));
-  ix = __fmaf_rn(P0, r, -0.5f);
-  iy = __fmaf_rn(P1, r, -0.5f);
-}
-
-// Anything left of -1 / right of W (above / below likewise) has all four taps out of bounds: clamp so
-// that cell coordinates stay small and NaN (fmaxf drops it) maps to "out of bounds" (exact walk only).
-__device__ __forceinline__ void clamp_pos(float& ix, float& iy, float xmax, float ymax) {
-  ix = fminf(fmaxf(ix, -2.0f), xmax);
-  iy = fminf(fmaxf(iy, -2.0f), ymax);
-}
-
-// <ref, src[tap]> over C channels: C/4 LDG.128 at immediate offsets from one address, packed FMAs.
-template <int C>
-__device__ __forceinline__ float tap_dot(const float4* __restrict__ s, const float2 (&ref2)[C / 2]) {
-  float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int c4 = 0; c4 < C / 4; ++c4) {
-    const float4 t = __ldg(s + c4 * 32);
-    s0 = __ffma2_rn(ref2[2 * c4 + 0], make_float2(t.x, t.y), s0);
-    s1 = __ffma2_rn(ref2[2 * c4 + 1], make_float2(t.z, t.w), s1);
-  }
-  return (s0.x + s0.y) + (s1.x + s1.y);
-}
-
-struct Tap {
-  float f, m, s;   // <ref, src>, source mu, source sigma at one integer source pixel (0 when outside)
-};
-
-template <int C, bool CW>
-__device__ __forceinline__ Tap load_tap(const float4* __restrict__ src_img, const float* __restrict__ gm,
-                                        const float2 (&ref2)[C / 2], int x, int y, int W, int H, int XB, int HW) {
-  Tap t;
-  t.f = t.m = t.s = 0.0f;
-  if (x >= 0 && x < W && y >= 0 && y < H) {
-    t.f = tap_dot<C>(src_img + ((y * XB + (x >> 5)) * (C / 4) * 32 + (x & 31)), ref2);
-    if (CW) {
-      t.m = ldg_f(gm + y * W + x);
-      t.s = ldg_f(gm + HW + y * W + x);
-    }
-  }
-  return t;
-}
-
-__device__ __forceinline__ float4 bilinear_poly(float v00, float v01, float v10, float v11) {
-  // v(fx,fy) = c0 + fx*cx + fy*(cy + fx*cxy)
-  return make_float4(v00, v01 - v00, v10 - v00, (v00 - v01) - (v10 - v11));
-}
-
-// Depth at which the projected sample crosses the vertical grid line ix == m (horizontal: swap the
-// roles of (a0,q0) and (a1,q1)):  (a0 + q0 d) / (a2 + q2 d) - 0.5 = m  =>  d = (c a2 - a0) / (q0 - c q2).
-// The position is a Moebius function of depth: a grid line beyond its asymptote is only "crossed" on the other
-// branch (behind the current depth) — such a line is never reached, so anything not ahead of `dcur` is +inf.
-__device__ __forceinline__ float crossing_depth(float m, float a_num, float q_num, float a2, float q2, float dcur) {
-  const float c = m + 0.5f;
-  const float num = __fmaf_rn(c, a2, -a_num);
-  const float den = __fmaf_rn(-c, q2, q_num);
-  const float d = den != 0.0f ? num * rcp_nr(den) : INFINITY;
-  return d >= __fmaf_rn(-1e-5f, fabsf(dcur), dcur) - 1e-12f ? d : INFINITY;
-}
-
-// Cell-list header: cell origin (as floats) and the index of the first hypothesis of the NEXT cell.
-__device__ __forceinline__ float4 make_hdr(float cx, float cy, int jnext) {
-  return make_float4(cx, cy, __int_as_float(jnext), 0.0f);
 }
 
 template <int C, int MODE, bool CW, bool REUSE>
@@ -198,7 +111,6 @@ cost_cells_kernel(const __grid_constant__ CostParams p, const int chunk) {
     ds.mu = ldg_f(p.ref_gmm + ((size_t)b * 2 + 0) * HW + n);
     ds.sg = ldg_f(p.ref_gmm + ((size_t)b * 2 + 1) * HW + n);
   }
-  const float xmax = (float)W + 1.0f, ymax = (float)H + 1.0f;
   const size_t img_stride4 = (size_t)H * XB * (C / 4) * 32;             // float4 per source image
 
   for (int j = 0; j < jc_end - jc; ++j) acc[j * NT + tid] = 0.0f;
@@ -206,9 +118,6 @@ cost_cells_kernel(const __grid_constant__ CostParams p, const int chunk) {
     for (int j = tid; j < jc_end - jc; j += NT) ks[j] = p.k[jc + j];
     __syncthreads();
   }
-  // The analytic walk needs depths that increase with j (sorted k, sigma > 0).
-  const bool lane_sorted = MODE == MAGNET_DEPTH_PLANES ? true : (ds.sg > 0.0f && ds.sg < 1e30f && fabsf(ds.mu) < 1e30f);
-  const bool can_walk = MODE != MAGNET_DEPTH_VOLUME && p.k_sorted != 0;
 
   for (int v = 0; v < p.V; ++v) {
     const magnet_camera* cam = p.cams + (b * p.V + v);
@@ -221,15 +130,7 @@ cost_cells_kernel(const __grid_constant__ CostParams p, const int chunk) {
     const float4* src_img = reinterpret_cast<const float4*>(p.src_feat) + (size_t)vb * img_stride4;
     const float* gm = CW ? p.src_gmm + (size_t)vb * 2 * HW : nullptr;
 
-    // Analytic walk is valid when every hypothesis of the chunk is in front of the source camera:
-    // z is linear in depth, so checking both ends suffices; ix(d), iy(d) are then monotone.
-    bool walk = false;
-    if (can_walk) {
-      const float zA = __fadd_rn(a2, __fmul_rn(q2, depth_of<MODE>(p, ds, jc)));
-      const float zB = __fadd_rn(a2, __fmul_rn(q2, depth_of<MODE>(p, ds, jc_end - 1)));
-      const bool ok = lane_sorted && zA > 1e-6f && zB > 1e-6f && zA < 1e30f && zB < 1e30f;
-      walk = __all_sync(FULL, ok);                                       // warp-uniform choice
-    }
+    const bool walk = __all_sync(FULL, walk_ok<MODE>(p, ds, jc, jc_end, a2, q2));   // warp-uniform choice
     // direction of travel of the sample as depth grows: sign of d(ix)/dd = (q0 a2 - a0 q2) / z^2
     const float gx = __fmaf_rn(q0, a2, -__fmul_rn(a0, q2)), gy = __fmaf_rn(q1, a2, -__fmul_rn(a1, q2));
     const int sx = gx > 0.0f ? 1 : (gx < 0.0f ? -1 : 0), sy = gy > 0.0f ? 1 : (gy < 0.0f ? -1 : 0);
@@ -243,73 +144,10 @@ cost_cells_kernel(const __grid_constant__ CostParams p, const int chunk) {
     int j_lo = jc;
     while (j_lo < jc_end) {                                              // rounds; warp-uniform
       // ---------------- phase A: cell list ----------------------------------------------------
-      int ncell = 0, j_stop = jc_end;
-      if (walk) {
-        // A-walk: step from grid line to grid line in depth space (the sample path is a straight line,
-        // monotone in depth); the first hypothesis of the next cell is found by binary search in the
-        // sorted k table.  The bilinear interpolant is continuous across cell edges, so a hypothesis that
-        // rounding puts on the "wrong" side of an edge changes the result by O(1e-6).
-        float ix, iy, z;
-        const float d_lo = depth_of<MODE>(p, ds, j_lo);
-        project(d_lo, a0, a1, a2, q0, q1, q2, ix, iy, z);
-        clamp_pos(ix, iy, xmax, ymax);
-        int x0 = min((int)floorf(ix), W), y0 = min((int)floorf(iy), H);          // in [-2, W] x [-2, H]
-        // next grid line in the direction of travel; lines exist only at -1..W (x) / -1..H (y)
-        int mx = sx > 0 ? x0 + 1 : x0, my = sy > 0 ? y0 + 1 : y0;
-        float dX = (sx != 0 && mx >= -1 && mx <= W) ? crossing_depth((float)mx, a0, q0, a2, q2, d_lo) : INFINITY;
-        float dY = (sy != 0 && my >= -1 && my <= H) ? crossing_depth((float)my, a1, q1, a2, q2, d_lo) : INFINITY;
-        const float inv_sg = MODE == MAGNET_DEPTH_GAUSS ? rcp_nr(ds.sg) : 1.0f;
-        int jcur = j_lo;
-        bool done = false;
-        while (__any_sync(FULL, !done)) {
-          if (!done) {
-            const float dn = fminf(dX, dY);
-            // first j in [jcur, jc_end) with depth_j >= dn  <=>  k_j >= kc
-            const float kc = MODE == MAGNET_DEPTH_GAUSS ? (dn - ds.mu) * inv_sg : dn;
-            int lo = jcur, hi = jc_end;
-            while (lo < hi) {
-              const int mid = (lo + hi) >> 1;
-              if (ks[mid - jc] < kc) lo = mid + 1; else hi = mid;
-            }
-            if (lo > jcur) {                                             // the cell holds hypotheses
-              hdr[ncell * NT + tid] = make_hdr((float)x0, (float)y0, lo);
-              ++ncell;
-              jcur = lo;
-            }
-            if (jcur >= jc_end) {
-              done = true;
-            } else if (ncell == NCELL) {
-              j_stop = jcur;
-              done = true;
-            } else if (dX <= dY) {
-              x0 += sx;
-              mx += sx;
-              dX = (mx >= -1 && mx <= W) ? crossing_depth((float)mx, a0, q0, a2, q2, dX) : INFINITY;
-            } else {
-              y0 += sy;
-              my += sy;
-              dY = (my >= -1 && my <= H) ? crossing_depth((float)my, a1, q1, a2, q2, dY) : INFINITY;
-            }
-          }
-        }
-      } else {
-        // A-exact: evaluate every hypothesis, record each change of cell (any depth order, any sign of z).
-        float cx = -1e30f, cy = -1e30f;
-        for (int j = j_lo; j < jc_end; ++j) {
-          float ix, iy, z;
-          project(depth_of<MODE>(p, ds, j), a0, a1, a2, q0, q1, q2, ix, iy, z);
-          clamp_pos(ix, iy, xmax, ymax);
-          const float fx = ix - cx, fy = iy - cy;
-          if (!(fx >= 0.0f && fx < 1.0f && fy >= 0.0f && fy < 1.0f)) {
-            if (ncell > 0) hdr[(ncell - 1) * NT + tid].z = __int_as_float(j);   // previous cell ends here
-            if (ncell == NCELL) { j_stop = j; break; }
-            cx = floorf(ix);
-            cy = floorf(iy);
-            hdr[ncell * NT + tid] = make_hdr(cx, cy, jc_end);
-            ++ncell;
-          }
-        }
-      }
+      int ncell, j_stop;
+      CellBox box;
+      cell_list<MODE, NCELL, NT>(p, ds, ks, hdr + tid, walk, jc, j_lo, jc_end, a0, a1, a2, q0, q1, q2, sx, sy, W, H,
+                                 ncell, j_stop, box);
       const int j_end = __reduce_min_sync(FULL, j_stop);
       const int nmax = __reduce_max_sync(FULL, ncell);
 

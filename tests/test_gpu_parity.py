@@ -16,7 +16,7 @@ from tests.util import compare_volume, golden_inputs, load_golden, oracle_cw
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [("direct", _lib.VARIANT_DIRECT), ("cells", _lib.VARIANT_CELLS)]
+VARIANTS = [("direct", _lib.VARIANT_DIRECT), ("cells", _lib.VARIANT_CELLS), ("window", _lib.VARIANT_WINDOW)]
 
 
 def _run_cw(inp, dvol, dev, variant):
@@ -63,7 +63,7 @@ def test_cw_vs_oracle_seeded(cuda, seed, depth, shape):
     dvol = inp.depth_volume()
     want, margin = oracle_cw(inp, dvol.numpy(), return_margin=True)
     for vname, variant in VARIANTS:
-        if variant == _lib.VARIANT_CELLS and shape["C"] not in (16, 32, 64):
+        if variant != _lib.VARIANT_DIRECT and shape["C"] not in (16, 32, 64):
             with pytest.raises(_lib.MagnetError):
                 _run_cw(inp, dvol, cuda, variant)
             continue
@@ -178,8 +178,10 @@ def test_full_size_properties_cfg2(cuda):
     plan = magnet_b200.MatchingPlan(g.ref_feat, g.nghbr_feat, g.nghbr_gmms, g.nghbr_poses, inp.is_valid,
                                     inp.cam_intrins, thres=5)
     k = inp.k.tolist()
-    cells = plan.cost(g.ref_gmms, k, variant=_lib.VARIANT_CELLS)
+    cells = plan.cost(g.ref_gmms, k, variant=_lib.VARIANT_WINDOW)
     direct = plan.cost(g.ref_gmms, k, variant=_lib.VARIANT_DIRECT)
+    assert torch.equal(plan.cost(g.ref_gmms, k, variant=_lib.VARIANT_CELLS), cells), \
+        "global-gather and window-staged kernels run the same arithmetic"
     assert torch.isfinite(cells).all()
     assert float(cells[3].abs().max()) == 0.0
     scale = float(direct.abs().max())
@@ -190,14 +192,14 @@ def test_full_size_properties_cfg2(cuda):
     assert frac_bad <= 3e-5
     plan2 = magnet_b200.MatchingPlan(g.ref_feat * 2.0, g.nghbr_feat, g.nghbr_gmms, g.nghbr_poses, inp.is_valid,
                                      inp.cam_intrins, thres=5)
-    assert torch.equal(plan2.cost(g.ref_gmms, k, variant=_lib.VARIANT_CELLS), cells * 2.0)
+    assert torch.equal(plan2.cost(g.ref_gmms, k, variant=_lib.VARIANT_WINDOW), cells * 2.0)
     # reverse the view order (features, Gaussians, poses, validity all permuted consistently)
     B, V = inp.B, inp.V
     perm = torch.arange(V - 1, -1, -1)
     idx = (perm[:, None] * B + torch.arange(B)[None]).reshape(-1).to(cuda)
     plan3 = magnet_b200.MatchingPlan(g.ref_feat, g.nghbr_feat[idx], g.nghbr_gmms[idx], g.nghbr_poses[:, perm.to(cuda)],
                                      inp.is_valid[:, perm], inp.cam_intrins, thres=5)
-    rev = plan3.cost(g.ref_gmms, k, variant=_lib.VARIANT_CELLS)
+    rev = plan3.cost(g.ref_gmms, k, variant=_lib.VARIANT_WINDOW)
     assert float((rev - cells).abs().max()) <= 2e-6 * scale
 
 

@@ -96,8 +96,8 @@ __device__ __forceinline__ float4 make_hdr(float cx, float cy, int jnext) {
 
 // Phase A for one lane: the list of bilinear cells the hypotheses [j_lo, jc_end) of this (pixel, view) fall
 // into, at most NCELLS per call.  Headers (cell origin, index of the first hypothesis of the next cell) go to
-// hdr[i * STRIDE]; returns the number of cells, the first hypothesis that is NOT covered (j_stop) and the
-// bounding box of the cell origins.
+// hdr[i * STRIDE]; returns the number of cells, the first hypothesis that is NOT covered (j_stop), the
+// bounding box of the cell origins and a bit mask of the hypotheses that start a cell (chunks of <= 32).
 //   walk == true : analytic walk from grid line to grid line in depth space (the sample path is a straight
 //     line, monotone in depth when every hypothesis is in front of the source camera); the first hypothesis
 //     of the next cell is found by binary search in the sorted k table `ks`.  The bilinear interpolant is
@@ -112,11 +112,12 @@ template <int MODE, int NCELLS, int STRIDE>
 __device__ __forceinline__ void cell_list(const CostParams& p, const DepthSrc<MODE>& ds, const float* __restrict__ ks,
                                           float4* __restrict__ hdr, bool walk, int jc, int j_lo, int jc_end,
                                           float a0, float a1, float a2, float q0, float q1, float q2, int sx, int sy,
-                                          int W, int H, int& ncell, int& j_stop, CellBox& box) {
+                                          int W, int H, int& ncell, int& j_stop, CellBox& box, unsigned& startmask) {
   const unsigned FULL = 0xffffffffu;
   const float xmax = (float)W + 1.0f, ymax = (float)H + 1.0f;
   ncell = 0;
   j_stop = jc_end;
+  startmask = 0u;                       // bit (j - jc) set <=> hypothesis j is the first one of a recorded cell
   box.x_lo = box.y_lo = 1 << 30;
   box.x_hi = box.y_hi = -(1 << 30);
   if (walk) {
@@ -144,6 +145,7 @@ __device__ __forceinline__ void cell_list(const CostParams& p, const DepthSrc<MO
         }
         if (lo > jcur) {                                                   // the cell holds hypotheses
           hdr[ncell * STRIDE] = make_hdr((float)x0, (float)y0, lo);
+          startmask |= 1u << ((jcur - jc) & 31);
           box.x_lo = min(box.x_lo, x0); box.x_hi = max(box.x_hi, x0);
           box.y_lo = min(box.y_lo, y0); box.y_hi = max(box.y_hi, y0);
           ++ncell;
@@ -178,6 +180,7 @@ __device__ __forceinline__ void cell_list(const CostParams& p, const DepthSrc<MO
         cx = floorf(ix);
         cy = floorf(iy);
         hdr[ncell * STRIDE] = make_hdr(cx, cy, jc_end);
+        startmask |= 1u << ((j - jc) & 31);
         box.x_lo = min(box.x_lo, (int)cx); box.x_hi = max(box.x_hi, (int)cx);
         box.y_lo = min(box.y_lo, (int)cy); box.y_hi = max(box.y_hi, (int)cy);
         ++ncell;

@@ -146,8 +146,9 @@ cost_cells_kernel(const __grid_constant__ CostParams p, const int chunk) {
       // ---------------- phase A: cell list ----------------------------------------------------
       int ncell, j_stop;
       CellBox box;
+      unsigned startmask;
       cell_list<MODE, NCELL, NT>(p, ds, ks, hdr + tid, walk, jc, j_lo, jc_end, a0, a1, a2, q0, q1, q2, sx, sy, W, H,
-                                 ncell, j_stop, box);
+                                 ncell, j_stop, box, startmask);
       const int j_end = __reduce_min_sync(FULL, j_stop);
       const int nmax = __reduce_max_sync(FULL, ncell);
 

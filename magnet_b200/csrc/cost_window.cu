@@ -152,8 +152,9 @@ cost_window_kernel(const __grid_constant__ CostParams p) {
       // ---------------- phase A: cell list + CTA bounding box ------------------------------------
       int ncell, j_stop;
       CellBox box;
+      unsigned startmask;
       cell_list<MODE, WNCELL, WNT>(p, ds, ks, hdr + tid, walk, jc, j_lo, jc_end, a0, a1, a2, q0, q1, q2, sx, sy, W, H,
-                                   ncell, j_stop, box);
+                                   ncell, j_stop, box, startmask);
       {
         const int xl = __reduce_min_sync(FULL, box.x_lo), xh = __reduce_max_sync(FULL, box.x_hi);
         const int yl = __reduce_min_sync(FULL, box.y_lo), yh = __reduce_max_sync(FULL, box.y_hi);
@@ -248,44 +249,37 @@ cost_window_kernel(const __grid_constant__ CostParams p) {
       }
 
       // ---------------- phase C: evaluate hypotheses [j_lo, j_end), accumulators in registers -------
-      {
-        float cx = 0.0f, cy = 0.0f;
-        int jnext = j_lo;                                                // forces the load of record 0
-        float4 rd = make_float4(0.f, 0.f, 0.f, 0.f), rm = rd, rs = rd;
-        const float4* hp = hdr + tid - WNT;
-        const float4* rp = rec + tid - 3 * WNT;
-#pragma unroll
-        for (int jj = 0; jj < WCHUNK; ++jj) {
-          const int j = jc + jj;
-          if (j >= j_lo && j < j_end) {                                  // CTA-uniform
-            float ix, iy, z;
-            project(depth_of<MODE>(p, ds, j), a0, a1, a2, q0, q1, q2, ix, iy, z);
-            if (j == jnext) {                                            // entering the lane's next cell
-              hp += WNT;
-              rp += 3 * WNT;
-              const float4 h = *hp;
-              cx = h.x;
-              cy = h.y;
-              jnext = __float_as_int(h.z);
-              rd = rp[0];
-              if (CW) {
-                rm = rp[WNT];
-                rs = rp[2 * WNT];
-              }
-            }
-            const float fx = ix - cx, fy = iy - cy;
-            float cost = __fmaf_rn(fy, __fmaf_rn(fx, rd.w, rd.z), __fmaf_rn(fx, rd.y, rd.x));
-            if (!(fabsf(cost) < 3.0e38f)) cost = 0.0f;                   // all-zero record x non-finite position
-            float val = cost;
-            if (CW) {
-              const float mu = __fmaf_rn(fy, __fmaf_rn(fx, rm.w, rm.z), __fmaf_rn(fx, rm.y, rm.x));
-              const float sg = __fmaf_rn(fy, __fmaf_rn(fx, rs.w, rs.z), __fmaf_rn(fx, rs.y, rs.x));
-              // homography.py:157-158: |z - mu~| < sigma~ * kappa, strict
-              val = (fabsf(__fsub_rn(z, mu)) < __fmul_rn(sg, p.kappa)) ? cost : 0.0f;
-            }
-            accr[jj] += val;
-          }
+      // Branch-free and chain-free: the index of the lane's cell at hypothesis j is the number of cell
+      // starts up to j (a popcount of the start mask from phase A), so every unrolled step is independent of
+      // the others; the record is simply (re)loaded each step — a lane enters a new cell on ~10 % of its
+      // steps, but some lane of the warp does on ~97 % of them, so a branch would be taken almost always.
+      auto step = [&](const int jj) {
+        float ix, iy, z;
+        project(depth_of<MODE>(p, ds, jc + jj), a0, a1, a2, q0, q1, q2, ix, iy, z);
+        const int ci = __popc(startmask & ((2u << jj) - 1u)) - 1;        // >= 0: bit (j_lo - jc) is always set
+        const int ro = ci * WNT + tid;
+        const float4 hc = hdr[ro];
+        const float4 rd = rec[3 * ro - 2 * tid];                         // rec[(3*ci + 0) * WNT + tid]
+        const float fx = ix - hc.x, fy = iy - hc.y;
+        float cost = __fmaf_rn(fy, __fmaf_rn(fx, rd.w, rd.z), __fmaf_rn(fx, rd.y, rd.x));
+        if (!(fabsf(cost) < 3.0e38f)) cost = 0.0f;                       // all-zero record x non-finite position
+        float val = cost;
+        if (CW) {
+          const float4 rm = rec[3 * ro - 2 * tid + WNT], rs = rec[3 * ro - 2 * tid + 2 * WNT];
+          const float mu = __fmaf_rn(fy, __fmaf_rn(fx, rm.w, rm.z), __fmaf_rn(fx, rm.y, rm.x));
+          const float sg = __fmaf_rn(fy, __fmaf_rn(fx, rs.w, rs.z), __fmaf_rn(fx, rs.y, rs.x));
+          // homography.py:157-158: |z - mu~| < sigma~ * kappa, strict
+          val = (fabsf(__fsub_rn(z, mu)) < __fmul_rn(sg, p.kappa)) ? cost : 0.0f;
         }
+        accr[jj] += val;
+      };
+      if (j_lo == jc && j_end == jc + WCHUNK) {                          // the usual case: one round, full chunk
+#pragma unroll
+        for (int jj = 0; jj < WCHUNK; ++jj) step(jj);
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < WCHUNK; ++jj)
+          if (jc + jj >= j_lo && jc + jj < j_end) step(jj);              // CTA-uniform guard
       }
       j_lo = j_end;
     }

@@ -1,5 +1,6 @@
 // C-ABI entry points declared in include/magnet_b200.h: argument validation + dispatch only.
 #include <atomic>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 
@@ -67,12 +68,11 @@ int validate_cost(const magnet_cost_args* a) {
 
 bool use_cells(const magnet_cost_args* a) {
   if (a->variant == MAGNET_VARIANT_DIRECT || a->variant == MAGNET_VARIANT_WINDOW) return false;
-  if (a->variant == MAGNET_VARIANT_AUTO) return false;     // AUTO prefers the window kernel, see use_window
   return magnet::cells_supports(a->C, a->D, a->src_layout);
 }
 
 bool use_window(const magnet_cost_args* a) {
-  if (a->variant != MAGNET_VARIANT_AUTO && a->variant != MAGNET_VARIANT_WINDOW) return false;
+  if (a->variant != MAGNET_VARIANT_WINDOW) return false;   // AUTO = global-gather cells kernel (faster today)
   return magnet::window_supports(a->C, a->D, a->src_layout);
 }
 }  // namespace
@@ -128,6 +128,7 @@ int magnet_cost_volume_f32(const magnet_cost_args* a, void* stream) {
   p.k_sorted = 1;
   for (int j = 1; j < a->D; ++j)
     if (!(p.k[j] >= p.k[j - 1])) p.k_sorted = 0;
+  if (getenv("MAGNET_NO_WALK")) p.k_sorted = 0;     // diagnostic: force the exact per-hypothesis cell walk
   int launches = 0;
   cudaError_t e;
   if (use_window(a) || use_cells(a)) {

@@ -88,15 +88,12 @@ __device__ __forceinline__ float crossing_depth(float m, float a_num, float q_nu
   return d >= __fmaf_rn(-1e-5f, fabsf(dcur), dcur) - 1e-12f ? d : INFINITY;
 }
 
-// Cell-list header: cell origin (as floats) and the index of the first hypothesis of the NEXT cell.
-__device__ __forceinline__ float4 make_hdr(float cx, float cy, int jnext) {
-  return make_float4(cx, cy, __int_as_float(jnext), 0.0f);
-}
+// Cell-list header: the cell origin (as floats).  Which hypotheses belong to which cell is carried by the
+// start mask that cell_list returns.
 
 
 // Phase A for one lane: the list of bilinear cells the hypotheses [j_lo, jc_end) of this (pixel, view) fall
-// into, at most NCELLS per call.  Headers (cell origin, index of the first hypothesis of the next cell) go to
-// hdr[i * STRIDE]; returns the number of cells, the first hypothesis that is NOT covered (j_stop), the
+// into, at most NCELLS per call.  Headers (cell origins) go to hdr[i * STRIDE]; returns the number of cells, the first hypothesis that is NOT covered (j_stop), the
 // bounding box of the cell origins and a bit mask of the hypotheses that start a cell (chunks of <= 32).
 //   walk == true : analytic walk from grid line to grid line in depth space (the sample path is a straight
 //     line, monotone in depth when every hypothesis is in front of the source camera); the first hypothesis
@@ -110,7 +107,7 @@ struct CellBox {
 
 template <int MODE, int NCELLS, int STRIDE>
 __device__ __forceinline__ void cell_list(const CostParams& p, const DepthSrc<MODE>& ds, const float* __restrict__ ks,
-                                          float4* __restrict__ hdr, bool walk, int jc, int j_lo, int jc_end,
+                                          float2* __restrict__ hdr, bool walk, int jc, int j_lo, int jc_end,
                                           float a0, float a1, float a2, float q0, float q1, float q2, int sx, int sy,
                                           int W, int H, int& ncell, int& j_stop, CellBox& box, unsigned& startmask) {
   const unsigned FULL = 0xffffffffu;
@@ -144,7 +141,7 @@ __device__ __forceinline__ void cell_list(const CostParams& p, const DepthSrc<MO
           if (ks[mid - jc] < kc) lo = mid + 1; else hi = mid;
         }
         if (lo > jcur) {                                                   // the cell holds hypotheses
-          hdr[ncell * STRIDE] = make_hdr((float)x0, (float)y0, lo);
+          hdr[ncell * STRIDE] = make_float2((float)x0, (float)y0);
           startmask |= 1u << ((jcur - jc) & 31);
           box.x_lo = min(box.x_lo, x0); box.x_hi = max(box.x_hi, x0);
           box.y_lo = min(box.y_lo, y0); box.y_hi = max(box.y_hi, y0);
@@ -175,11 +172,10 @@ __device__ __forceinline__ void cell_list(const CostParams& p, const DepthSrc<MO
       clamp_pos(ix, iy, xmax, ymax);
       const float fx = ix - cx, fy = iy - cy;
       if (!(fx >= 0.0f && fx < 1.0f && fy >= 0.0f && fy < 1.0f)) {
-        if (ncell > 0) hdr[(ncell - 1) * STRIDE].z = __int_as_float(j);       // previous cell ends here
         if (ncell == NCELLS) { j_stop = j; break; }
         cx = floorf(ix);
         cy = floorf(iy);
-        hdr[ncell * STRIDE] = make_hdr(cx, cy, jc_end);
+        hdr[ncell * STRIDE] = make_float2(cx, cy);
         startmask |= 1u << ((j - jc) & 31);
         box.x_lo = min(box.x_lo, (int)cx); box.x_hi = max(box.x_hi, (int)cx);
         box.y_lo = min(box.y_lo, (int)cy); box.y_hi = max(box.y_hi, (int)cy);

@@ -62,18 +62,20 @@ constexpr int NCELL = MAGNET_NCELL;    // cell records per lane per round
 constexpr int JCHUNK = MAGNET_JCHUNK;  // hypotheses per accumulation chunk (non-softmax variants)
 
 __host__ __device__ inline int cells_chunk(int D) { return D < JCHUNK ? D : JCHUNK; }
-// dynamic shared memory: rec[NCELL][3][NT] float4 | hdr[NCELL][NT] float4 | acc[chunk][NT] float | ks[chunk]
+// dynamic shared memory: rec[NCELL][3][NT] float4 | hdr[NCELL][NT] float2 | acc[chunk][NT] float | ks[chunk]
+// (kept as small as possible: what the CTAs do not take stays L1, and the tap gathers live on L1 hits)
 __host__ __device__ inline size_t cells_smem_bytes(int D) {
-  return (size_t)NCELL * 3 * NT * 16 + (size_t)NCELL * NT * 16 + (size_t)cells_chunk(D) * NT * 4 +
+  return (size_t)NCELL * 3 * NT * 16 + (size_t)NCELL * NT * 8 + (size_t)cells_chunk(D) * NT * 4 +
          (size_t)cells_chunk(D) * 4;
 }
+static_assert(JCHUNK <= 32, "the cell start mask of a chunk is one 32-bit word");
 
 template <int C, int MODE, bool CW, bool REUSE>
 __global__ void __launch_bounds__(NT, 4)
-cost_cells_kernel(const __grid_constant__ CostParams p, const int chunk) {
+cost_cells_kernel(const __grid_constant__ CostParams p, const int chunk, const int grid_chunks) {
   extern __shared__ float4 smem4[];
   float4* rec = smem4;                                                   // [NCELL][3][NT]
-  float4* hdr = smem4 + NCELL * 3 * NT;                                  // [NCELL][NT]
+  float2* hdr = reinterpret_cast<float2*>(smem4 + NCELL * 3 * NT);       // [NCELL][NT]
   float* acc = reinterpret_cast<float*>(hdr + NCELL * NT);               // [chunk][NT]
   float* ks = acc + chunk * NT;                                          // [chunk] k (or plane depth) table
 
@@ -82,10 +84,12 @@ cost_cells_kernel(const __grid_constant__ CostParams p, const int chunk) {
   const int H = p.H, W = p.W, HW = p.HW, D = p.D;
   const int XB = (W + 31) >> 5;
   const int tiles_x = (W + TILE_W - 1) / TILE_W;
-  const int tiles = tiles_x * ((H + TILE_H - 1) / TILE_H);
-  const int tile = blockIdx.x % tiles;
-  const int jc = (blockIdx.x / tiles) * chunk;                           // hypothesis chunk of this CTA
-  const int jc_end = min(jc + chunk, D);
+  // grid_chunks == number of chunks: one CTA per (tile, chunk), chunks of a tile adjacent (L2);
+  // grid_chunks == 1: one CTA per tile that loops over the chunks (source lines of chunk c are re-used from
+  // L1 / L2 by chunk c+1 of the same CTA).
+  const int tile = blockIdx.x / grid_chunks;
+  const int jc_first = (blockIdx.x % grid_chunks) * chunk;
+  const int jc_last = grid_chunks == 1 ? D : min(jc_first + chunk, D);
   const int px = (tile % tiles_x) * TILE_W + tid % TILE_W;
   const int py = (tile / tiles_x) * TILE_H + tid / TILE_W;
   const bool live = px < W && py < H;
@@ -113,8 +117,11 @@ cost_cells_kernel(const __grid_constant__ CostParams p, const int chunk) {
   }
   const size_t img_stride4 = (size_t)H * XB * (C / 4) * 32;             // float4 per source image
 
+  for (int jc = jc_first; jc < jc_last; jc += chunk) {
+  const int jc_end = min(jc + chunk, D);
   for (int j = 0; j < jc_end - jc; ++j) acc[j * NT + tid] = 0.0f;
   if (MODE != MAGNET_DEPTH_VOLUME) {
+    __syncthreads();                                                     // previous chunk done with ks
     for (int j = tid; j < jc_end - jc; j += NT) ks[j] = p.k[jc + j];
     __syncthreads();
   }
@@ -153,37 +160,75 @@ cost_cells_kernel(const __grid_constant__ CostParams p, const int chunk) {
       const int nmax = __reduce_max_sync(FULL, ncell);
 
       // ---------------- phase B: per-cell records ----------------------------------------------
+      // B1 — tap loop.  Every lane walks its OWN list of taps that are new w.r.t. its previous cell (an
+      // edge-adjacent cell brings 2, anything else 4) and the warp iterates until the longest list is done,
+      // one tap per lane per iteration.  Looping over cells instead (2 taps, plus 2 more "if any lane needs
+      // them") made the whole warp pay 4 taps on almost every cell: measured 25 dot products per lane where
+      // ~10 are needed.  Raw tap values go to the cell's record slot, component = corner (y*2 + x).
+      {
+        int ti = -1, cx0 = 0, cy0 = 0, lx = px0, ly = py0;
+        unsigned need = 0u;
+        bool active = ncell > 0;
+        while (__any_sync(FULL, active)) {
+          if (active) {
+            if (need == 0u) {                                            // next cell of this lane
+              if (++ti >= ncell) {
+                active = false;
+              } else {
+                const float2 h = hdr[ti * NT + tid];
+                cx0 = (int)h.x;
+                cy0 = (int)h.y;
+                const int dx = cx0 - lx, dy = cy0 - ly;
+                need = 0xFu;                                             // first cell / diagonal / jump
+                if (REUSE) {
+                  if (dy == 0) need = dx == 1 ? 0xAu : (dx == -1 ? 0x5u : (dx == 0 ? 0u : 0xFu));
+                  else if (dx == 0) need = dy == 1 ? 0xCu : (dy == -1 ? 0x3u : 0xFu);
+                }
+                lx = cx0;
+                ly = cy0;
+              }
+            }
+            if (active && need != 0u) {
+              const int c = __ffs(need) - 1;
+              need &= need - 1u;
+              const Tap t = load_tap<C, CW>(src_img, gm, ref2, cx0 + (c & 1), cy0 + (c >> 1), W, H, XB, HW);
+              float* slot = reinterpret_cast<float*>(rec + (ti * 3) * NT + tid) + c;
+              slot[0] = t.f;
+              if (CW) {
+                slot[4 * NT] = t.m;
+                slot[8 * NT] = t.s;
+              }
+            }
+          }
+        }
+      }
+      // B2 — fill the corners shared with the previous cell from registers, convert to polynomials.
       for (int i = 0; i < nmax; ++i) {
         if (i < ncell) {
-          const float4 h = hdr[i * NT + tid];
+          const float2 h = hdr[i * NT + tid];
           const int x0 = (int)h.x, y0 = (int)h.y;
           const int dx = x0 - px0, dy = y0 - py0;
-          const bool mvx = REUSE && dy == 0 && (dx == 1 || dx == -1);
-          const bool mvy = REUSE && dx == 0 && (dy == 1 || dy == -1);
-          // two taps every lane computes: the new column (x move), the new row (y move), or the top row
-          int ax = x0, ay = y0, bx = x0 + 1, by = y0;
-          if (mvx) { ax = bx = (dx == 1) ? x0 + 1 : x0; by = y0 + 1; }
-          if (mvy) { ay = by = (dy == 1) ? y0 + 1 : y0; }
-          const Tap tA = load_tap<C, CW>(src_img, gm, ref2, ax, ay, W, H, XB, HW);
-          const Tap tB = load_tap<C, CW>(src_img, gm, ref2, bx, by, W, H, XB, HW);
-          Tap n00, n01, n10, n11;
-          if (mvx) {
-            if (dx == 1) { n00 = p01; n10 = p11; n01 = tA; n11 = tB; }
-            else         { n01 = p00; n11 = p10; n00 = tA; n10 = tB; }
-          } else if (mvy) {
-            if (dy == 1) { n00 = p10; n01 = p11; n10 = tA; n11 = tB; }
-            else         { n10 = p00; n11 = p01; n00 = tA; n01 = tB; }
-          } else {                                                       // first cell / diagonal / jump
-            n00 = tA; n01 = tB;
-            n10 = load_tap<C, CW>(src_img, gm, ref2, x0, y0 + 1, W, H, XB, HW);
-            n11 = load_tap<C, CW>(src_img, gm, ref2, x0 + 1, y0 + 1, W, H, XB, HW);
-          }
-          p00 = n00; p01 = n01; p10 = n10; p11 = n11;
-          px0 = x0; py0 = y0;
-          rec[(i * 3 + 0) * NT + tid] = bilinear_poly(n00.f, n01.f, n10.f, n11.f);
+          float4 f = rec[(i * 3 + 0) * NT + tid], m = f, g = f;
           if (CW) {
-            rec[(i * 3 + 1) * NT + tid] = bilinear_poly(n00.m, n01.m, n10.m, n11.m);
-            rec[(i * 3 + 2) * NT + tid] = bilinear_poly(n00.s, n01.s, n10.s, n11.s);
+            m = rec[(i * 3 + 1) * NT + tid];
+            g = rec[(i * 3 + 2) * NT + tid];
+          }
+          if (REUSE) {
+            if (dy == 0 && dx == 1)       { f.x = p01.f; f.z = p11.f; m.x = p01.m; m.z = p11.m; g.x = p01.s; g.z = p11.s; }
+            else if (dy == 0 && dx == -1) { f.y = p00.f; f.w = p10.f; m.y = p00.m; m.w = p10.m; g.y = p00.s; g.w = p10.s; }
+            else if (dx == 0 && dy == 1)  { f.x = p10.f; f.y = p11.f; m.x = p10.m; m.y = p11.m; g.x = p10.s; g.y = p11.s; }
+            else if (dx == 0 && dy == -1) { f.z = p00.f; f.w = p01.f; m.z = p00.m; m.w = p01.m; g.z = p00.s; g.w = p01.s; }
+            else if (dx == 0 && dy == 0)  { f = make_float4(p00.f, p01.f, p10.f, p11.f); m = make_float4(p00.m, p01.m, p10.m, p11.m);
+                                            g = make_float4(p00.s, p01.s, p10.s, p11.s); }
+          }
+          p00.f = f.x; p01.f = f.y; p10.f = f.z; p11.f = f.w;
+          p00.m = m.x; p01.m = m.y; p10.m = m.z; p11.m = m.w;
+          p00.s = g.x; p01.s = g.y; p10.s = g.z; p11.s = g.w;
+          px0 = x0; py0 = y0;
+          rec[(i * 3 + 0) * NT + tid] = bilinear_poly(f.x, f.y, f.z, f.w);
+          if (CW) {
+            rec[(i * 3 + 1) * NT + tid] = bilinear_poly(m.x, m.y, m.z, m.w);
+            rec[(i * 3 + 2) * NT + tid] = bilinear_poly(g.x, g.y, g.z, g.w);
           }
         }
       }
@@ -191,22 +236,21 @@ cost_cells_kernel(const __grid_constant__ CostParams p, const int chunk) {
       // ---------------- phase C: evaluate hypotheses [j_lo, j_end) -----------------------------
       {
         float cx = 0.0f, cy = 0.0f;
-        int jnext = j_lo;                                                // forces the load of record 0
         float4 rd = make_float4(0.f, 0.f, 0.f, 0.f), rm = rd, rs = rd;
-        const float4* hp = hdr + tid - NT;
+        const float2* hp = hdr + tid - NT;
         const float4* rp = rec + tid - 3 * NT;
         float* ap = acc + (j_lo - jc) * NT + tid;
+        unsigned starts = startmask >> (j_lo - jc);                      // bit 0 <=> hypothesis j starts a cell
 #pragma unroll 4
-        for (int j = j_lo; j < j_end; ++j, ap += NT) {
+        for (int j = j_lo; j < j_end; ++j, ap += NT, starts >>= 1) {
           float ix, iy, z;
           project(depth_of<MODE>(p, ds, j), a0, a1, a2, q0, q1, q2, ix, iy, z);
-          if (j == jnext) {                                              // entering the lane's next cell
+          if (starts & 1u) {                                             // entering the lane's next cell
             hp += NT;
             rp += 3 * NT;
-            const float4 h = *hp;
+            const float2 h = *hp;
             cx = h.x;
             cy = h.y;
-            jnext = __float_as_int(h.z);
             rd = rp[0];
             if (CW) {
               rm = rp[NT];
@@ -240,6 +284,7 @@ cost_cells_kernel(const __grid_constant__ CostParams p, const int chunk) {
       for (int j = 0; j < cnt; ++j) outp[(size_t)j * HW] = __fdiv_rn(acc[j * NT + tid], p.vf);
     }
   }
+  }   // chunk loop
 }
 
 static int cells_grid_x(int H, int W) { return ((W + TILE_W - 1) / TILE_W) * ((H + TILE_H - 1) / TILE_H); }
@@ -260,7 +305,8 @@ template <int C, int MODE, bool REUSE>
 static cudaError_t launch_cm(const CostParams& p, bool cw, cudaStream_t st) {
   const size_t smem = cells_smem_bytes(p.D);
   const int chunk = cells_chunk(p.D), nchunks = (p.D + chunk - 1) / chunk;
-  dim3 grid(cells_grid_x(p.H, p.W) * nchunks, p.B), block(NT);
+  const int grid_chunks = getenv("MAGNET_CHUNK_LOOP") ? 1 : nchunks;
+  dim3 grid(cells_grid_x(p.H, p.W) * grid_chunks, p.B), block(NT);
   const int carve = cells_carveout_pct(smem);
 #define MAGNET_LAUNCH(CWv)                                                                              \
   do {                                                                                                  \
@@ -271,7 +317,7 @@ static cudaError_t launch_cm(const CostParams& p, bool cw, cudaStream_t st) {
       e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);            \
       if (e != cudaSuccess) return e;                                                                   \
     }                                                                                                   \
-    kern<<<grid, block, smem, st>>>(p, chunk);                                                          \
+    kern<<<grid, block, smem, st>>>(p, chunk, grid_chunks);                                                          \
     return cudaGetLastError();                                                                          \
   } while (0)
   if (cw) MAGNET_LAUNCH(true);

@@ -28,7 +28,7 @@ constexpr int WCHUNK = 32;            // hypotheses per CTA, accumulated in regi
 constexpr int WSMEM_MAX = 227 * 1024; // opt-in dynamic shared memory limit on sm_100
 
 __host__ __device__ constexpr size_t window_fixed_bytes() {
-  return (size_t)WNCELL * 3 * WNT * 16 + (size_t)WNCELL * WNT * 16 + WCHUNK * 4 + 2 * 8 * 4;
+  return (size_t)WNCELL * 3 * WNT * 16 + (size_t)WNCELL * WNT * 8 + WCHUNK * 4 + 2 * 8 * 4;
 }
 template <int C>
 __host__ __device__ constexpr int window_cap_px() {
@@ -74,7 +74,7 @@ cost_window_kernel(const __grid_constant__ CostParams p) {
   constexpr int QN = C / 4, PF4 = QN + 1;
   extern __shared__ float4 smem4[];
   float4* rec = smem4;                                                   // [WNCELL][3][WNT]
-  float4* hdr = smem4 + WNCELL * 3 * WNT;                                // [WNCELL][WNT]
+  float2* hdr = reinterpret_cast<float2*>(smem4 + WNCELL * 3 * WNT);     // [WNCELL][WNT]
   float* ks = reinterpret_cast<float*>(hdr + WNCELL * WNT);              // [WCHUNK]
   int* scr = reinterpret_cast<int*>(ks + WCHUNK);                        // [2][8] CTA reductions, double buffered
   float4* win = reinterpret_cast<float4*>(scr + 16);                     // [cap][PF4]
@@ -200,7 +200,7 @@ cost_window_kernel(const __grid_constant__ CostParams p) {
       const int nmax = __reduce_max_sync(FULL, ncell);
       for (int i = 0; i < nmax; ++i) {
         if (i < ncell) {
-          const float4 h = hdr[i * WNT + tid];
+          const float2 h = hdr[i * WNT + tid];
           const int x0 = (int)h.x, y0 = (int)h.y;
           const int dx = x0 - px0, dy = y0 - py0;
           const bool mvx = dy == 0 && (dx == 1 || dx == -1);
@@ -258,7 +258,7 @@ cost_window_kernel(const __grid_constant__ CostParams p) {
         project(depth_of<MODE>(p, ds, jc + jj), a0, a1, a2, q0, q1, q2, ix, iy, z);
         const int ci = __popc(startmask & ((2u << jj) - 1u)) - 1;        // >= 0: bit (j_lo - jc) is always set
         const int ro = ci * WNT + tid;
-        const float4 hc = hdr[ro];
+        const float2 hc = hdr[ro];
         const float4 rd = rec[3 * ro - 2 * tid];                         // rec[(3*ci + 0) * WNT + tid]
         const float fx = ix - hc.x, fy = iy - hc.y;
         float cost = __fmaf_rn(fy, __fmaf_rn(fx, rd.w, rd.z), __fmaf_rn(fx, rd.y, rd.x));

@@ -1,8 +1,6 @@
 #!/bin/bash
-# A/B matrix on the GPU box: tuning libs x resident CTAs per SM, kernel-only timing.
+# A/B on the GPU box, kernel-only timing.  usage: bash scripts/tune.sh <tag> "<env> <variant>" ...
 OUT=gpurun_out/${1:-tune}; mkdir -p $OUT; shift
-for v in window cells direct; do
-  timeout 300 python scripts/kbench.py cfg2 $v 20 2>&1 | tail -1 | tee -a $OUT/tune.txt
+for spec in "$@"; do
+  env $spec timeout 300 python scripts/kbench.py cfg2 $(echo $spec | grep -o 'VAR=[a-z]*' | cut -d= -f2) 20 2>&1 | tail -1 | sed "s|$| [$spec]|" | tee -a $OUT/tune.txt
 done
-timeout 300 python scripts/kbench.py cfg3 window 20 2>&1 | tail -1 | tee -a $OUT/tune.txt
-timeout 900 python -m pytest tests -m gpu -q -x > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 $OUT/pytest_gpu.log | cut -c1-250

@@ -67,13 +67,13 @@ def test_cost_args_validation_without_gpu():
 
 def test_launch_info_matches_design():
     from magnet_b200 import ops
-    grid, block, smem = ops.cost_launch_info(8, 4, 64, 64, 120, 160)     # AUTO -> window-staged kernel
+    grid, block, smem = ops.cost_launch_info(8, 4, 64, 64, 120, 160, variant=_lib.VARIANT_WINDOW)
     assert (grid, block) == (8 * 10 * 8 * 2, 256)                       # 16 x 16 pixel tiles x 2 chunks of 32 planes
-    fixed = 4 * 3 * 256 * 16 + 4 * 256 * 16 + 32 * 4 + 64
+    fixed = 4 * 3 * 256 * 16 + 4 * 256 * 8 + 32 * 4 + 64
     assert smem == fixed + ((227 * 1024 - fixed) // 272) * 272 and smem <= 227 * 1024
-    grid, block, smem = ops.cost_launch_info(8, 4, 64, 64, 120, 160, variant=_lib.VARIANT_CELLS)
+    grid, block, smem = ops.cost_launch_info(8, 4, 64, 64, 120, 160)     # AUTO -> cells kernel
     assert (grid, block) == (8 * 10 * 15 * 2, 128)                      # 16 x 8 pixel tiles x 2 chunks of 32 planes
-    assert smem == 4 * 3 * 128 * 16 + 4 * 128 * 16 + 32 * 128 * 4 + 32 * 4   # 4 records + headers + chunk + k
+    assert smem == 4 * 3 * 128 * 16 + 4 * 128 * 8 + 32 * 128 * 4 + 32 * 4    # 4 records + headers + chunk + k
     grid, block, smem = ops.cost_launch_info(8, 4, 64, 64, 120, 160, variant=_lib.VARIANT_DIRECT)
     assert (grid, block, smem) == (150 * 64 * 8, 128, 0)
 

@@ -160,75 +160,39 @@ cost_cells_kernel(const __grid_constant__ CostParams p, const int chunk, const i
       const int nmax = __reduce_max_sync(FULL, ncell);
 
       // ---------------- phase B: per-cell records ----------------------------------------------
-      // B1 — tap loop.  Every lane walks its OWN list of taps that are new w.r.t. its previous cell (an
-      // edge-adjacent cell brings 2, anything else 4) and the warp iterates until the longest list is done,
-      // one tap per lane per iteration.  Looping over cells instead (2 taps, plus 2 more "if any lane needs
-      // them") made the whole warp pay 4 taps on almost every cell: measured 25 dot products per lane where
-      // ~10 are needed.  Raw tap values go to the cell's record slot, component = corner (y*2 + x).
-      {
-        int ti = -1, cx0 = 0, cy0 = 0, lx = px0, ly = py0;
-        unsigned need = 0u;
-        bool active = ncell > 0;
-        while (__any_sync(FULL, active)) {
-          if (active) {
-            if (need == 0u) {                                            // next cell of this lane
-              if (++ti >= ncell) {
-                active = false;
-              } else {
-                const float2 h = hdr[ti * NT + tid];
-                cx0 = (int)h.x;
-                cy0 = (int)h.y;
-                const int dx = cx0 - lx, dy = cy0 - ly;
-                need = 0xFu;                                             // first cell / diagonal / jump
-                if (REUSE) {
-                  if (dy == 0) need = dx == 1 ? 0xAu : (dx == -1 ? 0x5u : (dx == 0 ? 0u : 0xFu));
-                  else if (dx == 0) need = dy == 1 ? 0xCu : (dy == -1 ? 0x3u : 0xFu);
-                }
-                lx = cx0;
-                ly = cy0;
-              }
-            }
-            if (active && need != 0u) {
-              const int c = __ffs(need) - 1;
-              need &= need - 1u;
-              const Tap t = load_tap<C, CW>(src_img, gm, ref2, cx0 + (c & 1), cy0 + (c >> 1), W, H, XB, HW);
-              float* slot = reinterpret_cast<float*>(rec + (ti * 3) * NT + tid) + c;
-              slot[0] = t.f;
-              if (CW) {
-                slot[4 * NT] = t.m;
-                slot[8 * NT] = t.s;
-              }
-            }
-          }
-        }
-      }
-      // B2 — fill the corners shared with the previous cell from registers, convert to polynomials.
+      // (A variant where every lane walks its own list of new taps, one or two per iteration, was measured:
+      // same number of gathers within 10 %, less memory-level parallelism, 12 % slower — see DESIGN.md.)
       for (int i = 0; i < nmax; ++i) {
         if (i < ncell) {
           const float2 h = hdr[i * NT + tid];
           const int x0 = (int)h.x, y0 = (int)h.y;
           const int dx = x0 - px0, dy = y0 - py0;
-          float4 f = rec[(i * 3 + 0) * NT + tid], m = f, g = f;
-          if (CW) {
-            m = rec[(i * 3 + 1) * NT + tid];
-            g = rec[(i * 3 + 2) * NT + tid];
+          const bool mvx = REUSE && dy == 0 && (dx == 1 || dx == -1);
+          const bool mvy = REUSE && dx == 0 && (dy == 1 || dy == -1);
+          // two taps every lane computes: the new column (x move), the new row (y move), or the top row
+          int ax = x0, ay = y0, bx = x0 + 1, by = y0;
+          if (mvx) { ax = bx = (dx == 1) ? x0 + 1 : x0; by = y0 + 1; }
+          if (mvy) { ay = by = (dy == 1) ? y0 + 1 : y0; }
+          const Tap tA = load_tap<C, CW>(src_img, gm, ref2, ax, ay, W, H, XB, HW);
+          const Tap tB = load_tap<C, CW>(src_img, gm, ref2, bx, by, W, H, XB, HW);
+          Tap n00, n01, n10, n11;
+          if (mvx) {
+            if (dx == 1) { n00 = p01; n10 = p11; n01 = tA; n11 = tB; }
+            else         { n01 = p00; n11 = p10; n00 = tA; n10 = tB; }
+          } else if (mvy) {
+            if (dy == 1) { n00 = p10; n01 = p11; n10 = tA; n11 = tB; }
+            else         { n10 = p00; n11 = p01; n00 = tA; n01 = tB; }
+          } else {                                                       // first cell / diagonal / jump
+            n00 = tA; n01 = tB;
+            n10 = load_tap<C, CW>(src_img, gm, ref2, x0, y0 + 1, W, H, XB, HW);
+            n11 = load_tap<C, CW>(src_img, gm, ref2, x0 + 1, y0 + 1, W, H, XB, HW);
           }
-          if (REUSE) {
-            if (dy == 0 && dx == 1)       { f.x = p01.f; f.z = p11.f; m.x = p01.m; m.z = p11.m; g.x = p01.s; g.z = p11.s; }
-            else if (dy == 0 && dx == -1) { f.y = p00.f; f.w = p10.f; m.y = p00.m; m.w = p10.m; g.y = p00.s; g.w = p10.s; }
-            else if (dx == 0 && dy == 1)  { f.x = p10.f; f.y = p11.f; m.x = p10.m; m.y = p11.m; g.x = p10.s; g.y = p11.s; }
-            else if (dx == 0 && dy == -1) { f.z = p00.f; f.w = p01.f; m.z = p00.m; m.w = p01.m; g.z = p00.s; g.w = p01.s; }
-            else if (dx == 0 && dy == 0)  { f = make_float4(p00.f, p01.f, p10.f, p11.f); m = make_float4(p00.m, p01.m, p10.m, p11.m);
-                                            g = make_float4(p00.s, p01.s, p10.s, p11.s); }
-          }
-          p00.f = f.x; p01.f = f.y; p10.f = f.z; p11.f = f.w;
-          p00.m = m.x; p01.m = m.y; p10.m = m.z; p11.m = m.w;
-          p00.s = g.x; p01.s = g.y; p10.s = g.z; p11.s = g.w;
+          p00 = n00; p01 = n01; p10 = n10; p11 = n11;
           px0 = x0; py0 = y0;
-          rec[(i * 3 + 0) * NT + tid] = bilinear_poly(f.x, f.y, f.z, f.w);
+          rec[(i * 3 + 0) * NT + tid] = bilinear_poly(n00.f, n01.f, n10.f, n11.f);
           if (CW) {
-            rec[(i * 3 + 1) * NT + tid] = bilinear_poly(m.x, m.y, m.z, m.w);
-            rec[(i * 3 + 2) * NT + tid] = bilinear_poly(g.x, g.y, g.z, g.w);
+            rec[(i * 3 + 1) * NT + tid] = bilinear_poly(n00.m, n01.m, n10.m, n11.m);
+            rec[(i * 3 + 2) * NT + tid] = bilinear_poly(n00.s, n01.s, n10.s, n11.s);
           }
         }
       }

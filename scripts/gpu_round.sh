@@ -28,7 +28,7 @@ tail -12 "$OUT/pytest_gpu.log" | cut -c1-300 | tee -a "$S"
 echo "== bench default" | tee -a "$S"
 timeout 900 python bench.py > "$OUT/bench.json" 2> "$OUT/bench.err"; echo "bench rc=$?" | tee -a "$S"; pick "$OUT/bench.json" | tee -a "$S"
 timeout 600 python bench.py --config cfg3 --no-cpu-baseline --steps 100 > "$OUT/bench_cfg3.json" 2>> "$OUT/bench.err"; echo "cfg3" | tee -a "$S"; pick "$OUT/bench_cfg3.json" | tee -a "$S"
-for v in cells_noreuse direct; do
+for v in cells_noreuse window direct; do
   timeout 600 python bench.py --variant $v --no-cpu-baseline --no-gnet --steps 20 --warmup 3 > "$OUT/bench_$v.json" 2>> "$OUT/bench.err"; echo "variant $v" | tee -a "$S"; pick "$OUT/bench_$v.json" | tee -a "$S"
 done
 for lib in "$@"; do

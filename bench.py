@@ -141,8 +141,12 @@ def cpu_reference_frames(frames_cfg, steps, warmup, threads=None, budget_s=None)
     Gaussian update, N_ITER iterations) on 1-frame batches of the same workload.  Returns (frames/s, info)."""
     from magnet_b200.synthetic import make_config
     from oracle import torch_ref
-    if threads:
-        torch.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm must use every host core it may run on
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    torch.set_num_threads(threads or avail)
     cores = torch.get_num_threads()
     inp = make_config(frames_cfg, seed=1, B=1)
     klist = [float(v) for v in inp.k.tolist()]
@@ -213,7 +217,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: magnet_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    md.init_process_group("nccl")
+    md.init_process_group("nccl", device_id=dev)
     K, W = max(1, args.steps), max(3, args.warmup)
 
     import magnet_b200
@@ -341,6 +345,7 @@ def main():
            "steps": ke}
 
     if rank != 0:
+        md.shutdown()
         return
     peak, peak_src = measured_peak()
     abytes = algorithmic_bytes(B, V, D, C, HW, fused=True)
@@ -367,6 +372,7 @@ def main():
         "with_gnet": with_gnet,
     }
     print(json.dumps(line), flush=True)
+    md.shutdown()
 
 
 if __name__ == "__main__":

@@ -18,15 +18,21 @@ def env_world() -> Tuple[int, int, int]:
             int(os.environ.get("WORLD_SIZE", 1)))
 
 
-def init_process_group(backend: str | None = None) -> Tuple[int, int, int]:
+def init_process_group(backend: str | None = None, device_id=None) -> Tuple[int, int, int]:
     rank, local_rank, world = env_world()
     if world > 1 and not dist.is_initialized():
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        kw = {"device_id": device_id} if (device_id is not None and backend == "nccl") else {}
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
     return rank, local_rank, world
+
+
+def shutdown() -> None:
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
 
 
 def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:

@@ -47,7 +47,7 @@ namespace magnet {
 #define MAGNET_DEFAULT_CTAS_PER_SM 0
 #endif
 #ifndef MAGNET_NCELL
-#define MAGNET_NCELL 4
+#define MAGNET_NCELL 5
 #endif
 #ifndef MAGNET_JCHUNK
 #define MAGNET_JCHUNK 32
@@ -70,8 +70,11 @@ __host__ __device__ inline size_t cells_smem_bytes(int D) {
 }
 static_assert(JCHUNK <= 32, "the cell start mask of a chunk is one 32-bit word");
 
+#ifndef MAGNET_MIN_CTAS
+#define MAGNET_MIN_CTAS 3   // 168 registers: more tap loads in flight per thread beats a 4th resident CTA
+#endif
 template <int C, int MODE, bool CW, bool REUSE>
-__global__ void __launch_bounds__(NT, 4)
+__global__ void __launch_bounds__(NT, MAGNET_MIN_CTAS)
 cost_cells_kernel(const __grid_constant__ CostParams p, const int chunk, const int grid_chunks) {
   extern __shared__ float4 smem4[];
   float4* rec = smem4;                                                   // [NCELL][3][NT]

@@ -73,7 +73,7 @@ def test_launch_info_matches_design():
     assert smem == fixed + ((227 * 1024 - fixed) // 272) * 272 and smem <= 227 * 1024
     grid, block, smem = ops.cost_launch_info(8, 4, 64, 64, 120, 160)     # AUTO -> cells kernel
     assert (grid, block) == (8 * 10 * 15 * 2, 128)                      # 16 x 8 pixel tiles x 2 chunks of 32 planes
-    assert smem == 4 * 3 * 128 * 16 + 4 * 128 * 8 + 32 * 128 * 4 + 32 * 4    # 4 records + headers + chunk + k
+    assert smem == 5 * 3 * 128 * 16 + 5 * 128 * 8 + 32 * 128 * 4 + 32 * 4    # 5 records + headers + chunk + k
     grid, block, smem = ops.cost_launch_info(8, 4, 64, 64, 120, 160, variant=_lib.VARIANT_DIRECT)
     assert (grid, block, smem) == (150 * 64 * 8, 128, 0)
 

@@ -56,17 +56,67 @@ __device__ __forceinline__ float tap_dot(const float4* __restrict__ s, const flo
 }
 
 
+// Two dot products <ref, src[tapA]>, <ref, src[tapB]> at once, loads issued in batches of 2 x QB channel quads
+// before their FMAs so that 2*QB LDG.128 per lane are in flight (the gathers mostly miss L1).
+template <int C, int QB>
+__device__ __forceinline__ void tap_dot2(const float4* __restrict__ sa, const float4* __restrict__ sb,
+                                         const float2 (&ref2)[C / 2], float& fa, float& fb) {
+  float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+#pragma unroll
+  for (int q0 = 0; q0 < C / 4; q0 += QB) {
+    float4 ta[QB], tb[QB];
+#pragma unroll
+    for (int q = 0; q < QB; ++q) {
+      ta[q] = __ldg(sa + (q0 + q) * 32);
+      tb[q] = __ldg(sb + (q0 + q) * 32);
+    }
+#pragma unroll
+    for (int q = 0; q < QB; ++q) {
+      a0 = __ffma2_rn(ref2[2 * (q0 + q) + 0], make_float2(ta[q].x, ta[q].y), a0);
+      a1 = __ffma2_rn(ref2[2 * (q0 + q) + 1], make_float2(ta[q].z, ta[q].w), a1);
+      b0 = __ffma2_rn(ref2[2 * (q0 + q) + 0], make_float2(tb[q].x, tb[q].y), b0);
+      b1 = __ffma2_rn(ref2[2 * (q0 + q) + 1], make_float2(tb[q].z, tb[q].w), b1);
+    }
+  }
+  fa = (a0.x + a0.y) + (a1.x + a1.y);
+  fb = (b0.x + b0.y) + (b1.x + b1.y);
+}
+
+// Two taps at once (see load_tap for the clamping convention).
+template <int C, bool CW>
+__device__ __forceinline__ void load_tap2(const float4* __restrict__ src_img, const float* __restrict__ gm,
+                                          const float2 (&ref2)[C / 2], int xa, int ya, int xb, int yb, int W, int H,
+                                          int XB, int HW, Tap& ta, Tap& tb) {
+  const bool ina = xa >= 0 && xa < W && ya >= 0 && ya < H, inb = xb >= 0 && xb < W && yb >= 0 && yb < H;
+  const int xac = min(max(xa, 0), W - 1), yac = min(max(ya, 0), H - 1);
+  const int xbc = min(max(xb, 0), W - 1), ybc = min(max(yb, 0), H - 1);
+  float ma = 0.f, sga = 0.f, mb = 0.f, sgb = 0.f;
+  if (CW) {
+    ma = ldg_f(gm + yac * W + xac); sga = ldg_f(gm + HW + yac * W + xac);
+    mb = ldg_f(gm + ybc * W + xbc); sgb = ldg_f(gm + HW + ybc * W + xbc);
+  }
+  float fa, fb;
+  tap_dot2<C, (C / 4 < 8 ? C / 4 : 8)>(src_img + ((yac * XB + (xac >> 5)) * (C / 4) * 32 + (xac & 31)),
+                                       src_img + ((ybc * XB + (xbc >> 5)) * (C / 4) * 32 + (xbc & 31)), ref2, fa, fb);
+  ta.f = ina ? fa : 0.0f; ta.m = ina ? ma : 0.0f; ta.s = ina ? sga : 0.0f;
+  tb.f = inb ? fb : 0.0f; tb.m = inb ? mb : 0.0f; tb.s = inb ? sgb : 0.0f;
+}
+
+// Branch-free: out-of-image taps are gathered from the clamped position and zeroed afterwards, so that the
+// loads of several taps can be in flight together (a per-tap `if` puts a reconvergence point between them).
 template <int C, bool CW>
 __device__ __forceinline__ Tap load_tap(const float4* __restrict__ src_img, const float* __restrict__ gm,
                                         const float2 (&ref2)[C / 2], int x, int y, int W, int H, int XB, int HW) {
+  const bool inb = x >= 0 && x < W && y >= 0 && y < H;
+  const int xc = min(max(x, 0), W - 1), yc = min(max(y, 0), H - 1);
   Tap t;
-  t.f = t.m = t.s = 0.0f;
-  if (x >= 0 && x < W && y >= 0 && y < H) {
-    t.f = tap_dot<C>(src_img + ((y * XB + (x >> 5)) * (C / 4) * 32 + (x & 31)), ref2);
-    if (CW) {
-      t.m = ldg_f(gm + y * W + x);
-      t.s = ldg_f(gm + HW + y * W + x);
-    }
+  const float f = tap_dot<C>(src_img + ((yc * XB + (xc >> 5)) * (C / 4) * 32 + (xc & 31)), ref2);
+  t.f = inb ? f : 0.0f;
+  t.m = t.s = 0.0f;
+  if (CW) {
+    const float m = ldg_f(gm + yc * W + xc), sg = ldg_f(gm + HW + yc * W + xc);
+    t.m = inb ? m : 0.0f;
+    t.s = inb ? sg : 0.0f;
   }
   return t;
 }

@@ -176,8 +176,8 @@ cost_cells_kernel(const __grid_constant__ CostParams p, const int chunk, const i
           int ax = x0, ay = y0, bx = x0 + 1, by = y0;
           if (mvx) { ax = bx = (dx == 1) ? x0 + 1 : x0; by = y0 + 1; }
           if (mvy) { ay = by = (dy == 1) ? y0 + 1 : y0; }
-          const Tap tA = load_tap<C, CW>(src_img, gm, ref2, ax, ay, W, H, XB, HW);
-          const Tap tB = load_tap<C, CW>(src_img, gm, ref2, bx, by, W, H, XB, HW);
+          Tap tA, tB;
+          load_tap2<C, CW>(src_img, gm, ref2, ax, ay, bx, by, W, H, XB, HW, tA, tB);
           Tap n00, n01, n10, n11;
           if (mvx) {
             if (dx == 1) { n00 = p01; n10 = p11; n01 = tA; n11 = tB; }
@@ -187,8 +187,7 @@ cost_cells_kernel(const __grid_constant__ CostParams p, const int chunk, const i
             else         { n10 = p00; n11 = p01; n00 = tA; n01 = tB; }
           } else {                                                       // first cell / diagonal / jump
             n00 = tA; n01 = tB;
-            n10 = load_tap<C, CW>(src_img, gm, ref2, x0, y0 + 1, W, H, XB, HW);
-            n11 = load_tap<C, CW>(src_img, gm, ref2, x0 + 1, y0 + 1, W, H, XB, HW);
+            load_tap2<C, CW>(src_img, gm, ref2, x0, y0 + 1, x0 + 1, y0 + 1, W, H, XB, HW, n10, n11);
           }
           p00 = n00; p01 = n01; p10 = n10; p11 = n11;
           px0 = x0; py0 = y0;

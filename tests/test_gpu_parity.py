@@ -218,3 +218,29 @@ def test_full_size_identity_known_answer_cfg3(cuda):
     dots = torch.stack([(g.ref_feat * g.nghbr_feat[v * B:(v + 1) * B]).sum(1) for v in range(V)]).mean(0)
     err = (got - dots[:, None]).abs().max()
     assert float(err) <= 1e-4 * float(dots.abs().max())
+
+
+def test_head_training_step_decreases_loss(cuda):
+    """configs[3] in miniature: the head (G-Net + mask head + upsampling) trains through the kernels: gradients
+    reach every trainable parameter and a few AdamW steps reduce the Gaussian NLL."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("train_head", os.path.join(os.path.dirname(os.path.dirname(__file__)), "examples", "train_head.py"))
+    th = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(th)
+    inp = make_inputs(B=2, V=2, D=8, H=24, W=32, C=16, seed=51, depth="smooth").to(cuda)
+    torch.manual_seed(0)
+    head = magnet_b200.MagnetHead(n_samples=8, n_iter=2).to(cuda)
+    x_d3 = torch.randn(2, 256, 24, 32, device=cuda)
+    gt = torch.nn.functional.interpolate(inp.ref_gmms[:, 0:1] * 1.05, scale_factor=4, mode="nearest")
+    opt = torch.optim.AdamW(head.parameters(), lr=1e-3)
+    losses = []
+    for _ in range(6):
+        preds = head(inp.ref_feat, inp.nghbr_feat, inp.ref_gmms, inp.nghbr_gmms, x_d3, inp.nghbr_poses, inp.is_valid, inp.cam_intrins)
+        assert len(preds) == 2 and preds[0].shape == (2, 2, 96, 128)
+        loss = th.gaussian_nll(preds, gt, gt > 0)
+        opt.zero_grad()
+        loss.backward()
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in head.parameters())
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0]

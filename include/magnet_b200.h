@@ -113,6 +113,23 @@ int magnet_cost_launch_info(const magnet_cost_args* args, int* grid_ctas, int* b
 int magnet_cost_volume_f32(const magnet_cost_args* args, void* stream);
 
 /*
+ * Backward of the plane-sweep volume (est_costvolume_F) w.r.t. both feature maps — what autograd derives for
+ * homography.py:10-75 during F-Net training (train_FNet.py:95-114): through the softmax, the 1/V mean, the channel
+ * dot product and grid_sample's bilinear gather (scatter-add into the source features).
+ * Geometry fields of `fwd` as in the forward call (consistency must be 0, depth_mode MAGNET_DEPTH_PLANES,
+ * src_layout MAGNET_SRC_NCHW, C in {8,16,32,64}); `fwd->out` is ignored.
+ */
+typedef struct magnet_cost_f_bwd_args {
+  const magnet_cost_args* fwd;
+  const float* prob;      /* (B,D,H,W) forward output; used when fwd->softmax == 1                          */
+  const float* grad_out;  /* (B,D,H,W) gradient w.r.t. the forward output                                   */
+  float* workspace;       /* (B,D,H,W) scratch (gradient w.r.t. the pre-softmax scores)                     */
+  float* grad_ref;        /* (B,C,H,W)   written                                                            */
+  float* grad_src;        /* (V*B,C,H,W) NCHW, ACCUMULATED with atomics: the caller zeroes it               */
+} magnet_cost_f_bwd_args;
+int magnet_cost_volume_f_bwd_f32(const magnet_cost_f_bwd_args* args, void* stream);
+
+/*
  * Camera constants.  Replaces homography.py:89,98-102 (IntM/R/t products, done there per pair per
  * iteration).  intM (B,3,3) dense; R and t are addressed with element strides so that the
  * non-contiguous views nghbr_poses[:,:,:3,:3] / [:,:,:3,3] of MAGNET.py:147-148 can be passed as is:

@@ -26,7 +26,7 @@ VARIANT_AUTO, VARIANT_DIRECT, VARIANT_CELLS, VARIANT_CELLS_NOREUSE, VARIANT_WIND
 # every symbol include/magnet_b200.h declares (tests check the library exports all of them)
 EXPORTS = (
     "magnet_abi_version", "magnet_strerror", "magnet_last_cuda_error", "magnet_launch_count",
-    "magnet_cost_launch_info", "magnet_cost_volume_f32", "magnet_pack_cameras_f32",
+    "magnet_cost_launch_info", "magnet_cost_volume_f32", "magnet_cost_volume_f_bwd_f32", "magnet_pack_cameras_f32",
     "magnet_repack_tiled32_f32", "magnet_sample_depths_f32", "magnet_gaussian_update_fwd_f32",
     "magnet_gaussian_update_bwd_f32",
 )
@@ -42,6 +42,12 @@ class CostArgs(C.Structure):
         ("cams", C.c_void_p), ("d_volume", C.c_void_p), ("ref_gmm", C.c_void_p), ("k_host", C.c_void_p),
         ("out", C.c_void_p),
     ]
+
+
+class CostFBwdArgs(C.Structure):
+    """Mirror of ``struct magnet_cost_f_bwd_args``."""
+    _fields_ = [("fwd", C.POINTER(CostArgs)), ("prob", C.c_void_p), ("grad_out", C.c_void_p), ("workspace", C.c_void_p),
+                ("grad_ref", C.c_void_p), ("grad_src", C.c_void_p)]
 
 
 class MagnetError(RuntimeError):
@@ -73,6 +79,8 @@ def lib() -> C.CDLL:
     L.magnet_cost_launch_info.argtypes = [C.POINTER(CostArgs), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.magnet_cost_volume_f32.restype = C.c_int
     L.magnet_cost_volume_f32.argtypes = [C.POINTER(CostArgs), C.c_void_p]
+    L.magnet_cost_volume_f_bwd_f32.restype = C.c_int
+    L.magnet_cost_volume_f_bwd_f32.argtypes = [C.POINTER(CostFBwdArgs), C.c_void_p]
     L.magnet_pack_cameras_f32.restype = C.c_int
     L.magnet_pack_cameras_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                           C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int32,

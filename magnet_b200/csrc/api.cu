@@ -25,6 +25,22 @@ cudaError_t launch_sample(const float* gmm, const float* k_host, int B, int D, i
 cudaError_t launch_update_fwd(const float* dout, const float* gmm0, int B, int HW, float* out, cudaStream_t st);
 cudaError_t launch_update_bwd(const float* gout, const float* dout, const float* gmm0, int B, int HW, float* gin,
                               cudaStream_t st);
+struct BwdParams {
+  int B, V, D, C, H, W, HW;
+  int softmax;
+  float vf;
+  const float* ref_feat;
+  const float* src_feat;
+  const float* rays;
+  const magnet_camera* cams;
+  const float* prob;
+  const float* grad_out;
+  float* g_score;
+  float* grad_ref;
+  float* grad_src;
+  float k[MAGNET_MAX_PLANES];
+};
+cudaError_t launch_cost_f_bwd(const BwdParams& p, cudaStream_t st, int* launches);
 }  // namespace magnet
 
 namespace {
@@ -146,6 +162,31 @@ int magnet_cost_volume_f32(const magnet_cost_args* a, void* stream) {
     e = magnet::launch_cost_direct(p, a->depth_mode, a->src_layout, a->C, a->consistency != 0, a->softmax != 0,
                                    (cudaStream_t)stream, &launches);
   }
+  if (e != cudaSuccess) return cuda_fail(e);
+  g_launches += launches;
+  return MAGNET_OK;
+}
+
+int magnet_cost_volume_f_bwd_f32(const magnet_cost_f_bwd_args* b, void* stream) {
+  if (!b || !b->fwd) return MAGNET_ERR_NULL;
+  const magnet_cost_args* a = b->fwd;
+  if (a->B <= 0 || a->V <= 0 || a->D <= 0 || a->C <= 0 || a->H <= 0 || a->W <= 0) return MAGNET_ERR_SHAPE;
+  if (a->D > MAGNET_MAX_PLANES) return MAGNET_ERR_UNSUPPORTED;
+  if (!a->ref_feat || !a->src_feat || !a->rays || !a->cams || !a->k_host) return MAGNET_ERR_NULL;
+  if (!b->grad_out || !b->workspace || !b->grad_ref || !b->grad_src) return MAGNET_ERR_NULL;
+  if (a->softmax && !b->prob) return MAGNET_ERR_NULL;
+  if (a->consistency || a->depth_mode != MAGNET_DEPTH_PLANES || a->src_layout != MAGNET_SRC_NCHW)
+    return MAGNET_ERR_UNSUPPORTED;
+  if (a->C != 8 && a->C != 16 && a->C != 32 && a->C != 64) return MAGNET_ERR_UNSUPPORTED;
+  magnet::BwdParams p;
+  p.B = a->B; p.V = a->V; p.D = a->D; p.C = a->C; p.H = a->H; p.W = a->W; p.HW = a->H * a->W;
+  p.softmax = a->softmax != 0;
+  p.vf = (float)a->V;
+  p.ref_feat = a->ref_feat; p.src_feat = a->src_feat; p.rays = a->rays; p.cams = a->cams;
+  p.prob = b->prob; p.grad_out = b->grad_out; p.g_score = b->workspace; p.grad_ref = b->grad_ref; p.grad_src = b->grad_src;
+  for (int j = 0; j < MAGNET_MAX_PLANES; ++j) p.k[j] = j < a->D ? a->k_host[j] : 0.0f;
+  int launches = 0;
+  cudaError_t e = magnet::launch_cost_f_bwd(p, (cudaStream_t)stream, &launches);
   if (e != cudaSuccess) return cuda_fail(e);
   g_launches += launches;
   return MAGNET_OK;

@@ -14,7 +14,7 @@ per-(batch, view) Python loop):
   * ``nghbr_feat`` arrives NCHW: repacked once per forward into the (N, C/4, H, W, 4) layout the
     tap-sharing kernel gathers from (cached the same way).
 The CW volume is not differentiable (its inputs never require grad in the reference, SURVEY §3.2);
-the F volume provides a backward for F-Net training.
+the F volume is differentiable w.r.t. both feature maps (magnet_cost_volume_f_bwd_f32) for F-Net training.
 """
 from __future__ import annotations
 
@@ -127,22 +127,23 @@ def est_costvolume_CW(d_volume, ref_feat, nghbr_feat, ref_gmms, nghbr_gmms,
 
 
 class _CostVolumeF(torch.autograd.Function):
-    """Plane-sweep probability volume for F-Net training (homography.py:10-75)."""
+    """Plane-sweep probability volume for F-Net training (homography.py:10-75), forward + backward kernels."""
 
     @staticmethod
     def forward(ctx, ref_feat, nghbr_feat, planes, rays_d, cams, V, variant):
         src, layout = _packed_source(nghbr_feat.detach())
         out = ops.cost_volume(ref_feat.detach(), src, rays_d, cams, V=V, src_layout=layout, consistency=False,
                               k=planes, planes=True, softmax=True, variant=variant)
-        ctx.mark_non_differentiable()
-        ctx.needs_bwd = ref_feat.requires_grad or nghbr_feat.requires_grad
+        ctx.save_for_backward(ref_feat.detach(), nghbr_feat.detach(), out, rays_d, cams)
+        ctx.planes, ctx.V = planes, V
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        raise _lib.MagnetError(
-            "est_costvolume_F backward (bilinear scatter into the source features) is SURVEY §8 row f-1, "
-            "scheduled after the CW path; it is not implemented in this round — there is no PyTorch fallback")
+        ref_feat, nghbr_feat, out, rays_d, cams = ctx.saved_tensors
+        g_ref, g_src = ops.cost_volume_f_bwd(ref_feat, nghbr_feat, rays_d, cams, ctx.planes, ctx.V, out,
+                                             grad_out.contiguous(), softmax=True)
+        return g_ref, g_src, None, None, None, None, None
 
 
 def est_costvolume_F(d_center, ref_feat, nghbr_feat, R, t, is_valid, cam_intrins, variant=_lib.VARIANT_AUTO):

@@ -131,6 +131,33 @@ def cost_volume(ref_feat: torch.Tensor, src_feat: torch.Tensor, rays: torch.Tens
     return out
 
 
+def cost_volume_f_bwd(ref_feat, src_feat_nchw, rays, cams, planes, V, prob, grad_out, softmax=True):
+    """Gradients of the plane-sweep volume w.r.t. (ref_feat, src_feat) — one magnet_cost_volume_f_bwd_f32 call.
+    src_feat_nchw (V*B,C,H,W) view-major; prob = forward output; returns (grad_ref, grad_src) in NCHW."""
+    ref_feat = _need_cuda_f32("ref_feat", ref_feat)
+    src = _need_cuda_f32("src_feat", src_feat_nchw)
+    rays = _need_cuda_f32("rays", rays)
+    cams = _need_cuda_f32("cams", cams)
+    prob = _need_cuda_f32("prob", prob)
+    grad_out = _need_cuda_f32("grad_out", grad_out)
+    B, Cc, H, W = ref_feat.shape
+    karr = planes if isinstance(planes, C.Array) else k_array(planes)
+    a = CostArgs()
+    a.B, a.V, a.D, a.C, a.H, a.W = B, V, len(karr), Cc, H, W
+    a.depth_mode, a.src_layout, a.consistency, a.softmax = _lib.DEPTH_PLANES, _lib.SRC_NCHW, 0, 1 if softmax else 0
+    a.ref_feat, a.src_feat, a.rays, a.cams = ref_feat.data_ptr(), src.data_ptr(), rays.data_ptr(), cams.data_ptr()
+    a.k_host = C.cast(karr, C.c_void_p)
+    work = torch.empty_like(prob)
+    g_ref = torch.empty_like(ref_feat)
+    g_src = torch.zeros_like(src)
+    bw = _lib.CostFBwdArgs()
+    bw.fwd = C.pointer(a)
+    bw.prob, bw.grad_out, bw.workspace = prob.data_ptr(), grad_out.data_ptr(), work.data_ptr()
+    bw.grad_ref, bw.grad_src = g_ref.data_ptr(), g_src.data_ptr()
+    check(lib().magnet_cost_volume_f_bwd_f32(C.byref(bw), _stream()), "magnet_cost_volume_f_bwd_f32")
+    return g_ref, g_src
+
+
 def cost_launch_info(B, V, D, Cc, H, W, variant=_lib.VARIANT_AUTO):
     """(grid CTAs, threads per CTA, dynamic smem bytes) the cost kernel would use for these sizes."""
     a = CostArgs()

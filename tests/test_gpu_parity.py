@@ -244,3 +244,25 @@ def test_head_training_step_decreases_loss(cuda):
         opt.step()
         losses.append(float(loss))
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("seed,shape", [(61, dict(B=2, V=2, D=8, H=20, W=28, C=16)), (62, dict(B=1, V=3, D=12, H=16, W=40, C=64))])
+def test_f_volume_backward_matches_autograd_of_reference_ops(cuda, seed, shape):
+    """gradients of est_costvolume_F w.r.t. both feature maps against autograd through the ATen port
+    of the reference (same operator sequence as homography.py:10-75, run on the same device)."""
+    from oracle import torch_ref
+    inp = make_inputs(seed=seed, depth="smooth", invalid=[(0, 1)], **shape)
+    g = inp.to(cuda)
+    planes = torch.linspace(0.8, 6.0, 10, device=cuda).view(1, -1, 1, 1)
+    gout = torch.randn(shape["B"], 10, shape["H"], shape["W"], device=cuda)
+    r1, s1 = g.ref_feat.clone().requires_grad_(True), g.nghbr_feat.clone().requires_grad_(True)
+    ours = magnet_b200.est_costvolume_F(planes, r1, s1, g.R, g.t, inp.is_valid, inp.cam_intrins)
+    (ours * gout).sum().backward()
+    r2, s2 = g.ref_feat.clone().requires_grad_(True), g.nghbr_feat.clone().requires_grad_(True)
+    cam_d = {k: v.to(cuda) for k, v in inp.cam_intrins.items()}
+    theirs = torch_ref.cost_volume_f(planes, r2, s2, g.R, g.t, inp.is_valid, cam_d)
+    (theirs * gout).sum().backward()
+    assert float((ours - theirs).abs().max()) <= 1e-4 * float(theirs.abs().max())
+    for a, b, name in ((r1.grad, r2.grad, "ref"), (s1.grad, s2.grad, "src")):
+        err = float((a - b).abs().max())
+        assert err <= 2e-4 * float(b.abs().max()), (name, err, float(b.abs().max()))

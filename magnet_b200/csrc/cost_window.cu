@@ -13,19 +13,32 @@
 //   3. runs phase B against the window: a 64-channel dot product is 16 LDS.128 at immediate offsets
 //      (pixel stride 17 float4 = 272 B makes the quarter-warp accesses bank-conflict free) + 32 FFMA2,
 //   4. runs phase C with the 32 accumulators in registers (fully unrolled, no shared-memory column).
-// One CTA per SM (8 warps, up to 255 registers per thread); the window gets all shared memory that the
-// records leave (~600 pixels).  A window that does not fit falls back to global gathers for that round.
+// Two CTAs of 128 threads (16x8 tiles) per SM, up to 255 registers per thread; the window gets the shared
+// memory that the records leave (~300 pixels per CTA).  A window that does not fit falls back to global
+// gathers for that round.  Measured (cfg2): 0.54 ms vs 0.35 ms for the global-gather kernel — it moves 2.5x
+// fewer bytes L2 -> SM but with 8 warps per SM it cannot hide the shared-memory / barrier latencies; it is
+// kept as MAGNET_VARIANT_WINDOW for the next round.
 #include <cstdlib>
 
 #include "cells_common.cuh"
 
 namespace magnet {
 
-constexpr int WNT = 256;              // threads per CTA
-constexpr int WTW = 16, WTH = 16;     // CTA tile (pixels)
-constexpr int WNCELL = 4;             // cell records per lane per round
+#ifndef MAGNET_WNT
+#define MAGNET_WNT 128
+#endif
+#ifndef MAGNET_WCTAS
+#define MAGNET_WCTAS 2
+#endif
+#ifndef MAGNET_WNCELL
+#define MAGNET_WNCELL 5
+#endif
+constexpr int WNT = MAGNET_WNT;       // threads per CTA
+constexpr int WTW = 16, WTH = WNT / 16;  // CTA tile (pixels)
+constexpr int WCTAS = MAGNET_WCTAS;   // resident CTAs per SM the shared memory is budgeted for
+constexpr int WNCELL = MAGNET_WNCELL; // cell records per lane per round
 constexpr int WCHUNK = 32;            // hypotheses per CTA, accumulated in registers
-constexpr int WSMEM_MAX = 227 * 1024; // opt-in dynamic shared memory limit on sm_100
+constexpr int WSMEM_MAX = (227 * 1024) / WCTAS - (WCTAS > 1 ? 1024 : 0);  // dynamic smem per CTA (sm_100: 227 KB/SM)
 
 __host__ __device__ constexpr size_t window_fixed_bytes() {
   return (size_t)WNCELL * 3 * WNT * 16 + (size_t)WNCELL * WNT * 8 + WCHUNK * 4 + 2 * 8 * 4;
@@ -69,7 +82,7 @@ __device__ __forceinline__ Tap load_tap_win(const float4* __restrict__ win, cons
 }
 
 template <int C, int MODE, bool CW>
-__global__ void __launch_bounds__(WNT, 1)
+__global__ void __launch_bounds__(WNT, WCTAS)
 cost_window_kernel(const __grid_constant__ CostParams p) {
   constexpr int QN = C / 4, PF4 = QN + 1;
   extern __shared__ float4 smem4[];

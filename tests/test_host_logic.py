@@ -68,9 +68,10 @@ def test_cost_args_validation_without_gpu():
 def test_launch_info_matches_design():
     from magnet_b200 import ops
     grid, block, smem = ops.cost_launch_info(8, 4, 64, 64, 120, 160, variant=_lib.VARIANT_WINDOW)
-    assert (grid, block) == (8 * 10 * 8 * 2, 256)                       # 16 x 16 pixel tiles x 2 chunks of 32 planes
-    fixed = 4 * 3 * 256 * 16 + 4 * 256 * 8 + 32 * 4 + 64
-    assert smem == fixed + ((227 * 1024 - fixed) // 272) * 272 and smem <= 227 * 1024
+    assert (grid, block) == (8 * 10 * 15 * 2, 128)                      # 16 x 8 pixel tiles x 2 chunks of 32 planes
+    fixed = 5 * 3 * 128 * 16 + 5 * 128 * 8 + 32 * 4 + 64
+    budget = (227 * 1024) // 2 - 1024                                   # two CTAs per SM
+    assert smem == fixed + ((budget - fixed) // 272) * 272 and smem <= budget
     grid, block, smem = ops.cost_launch_info(8, 4, 64, 64, 120, 160)     # AUTO -> cells kernel
     assert (grid, block) == (8 * 10 * 15 * 2, 128)                      # 16 x 8 pixel tiles x 2 chunks of 32 planes
     assert smem == 5 * 3 * 128 * 16 + 5 * 128 * 8 + 32 * 128 * 4 + 32 * 4    # 5 records + headers + chunk + k

@@ -141,12 +141,19 @@ def cpu_reference_frames(frames_cfg, steps, warmup, threads=None, budget_s=None)
     Gaussian update, N_ITER iterations) on 1-frame batches of the same workload.  Returns (frames/s, info)."""
     from magnet_b200.synthetic import make_config
     from oracle import torch_ref
-    # torchrun exports OMP_NUM_THREADS=1; the CPU arm must use every host core it may run on
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm must use every host core it may run on.  One thread per
+    # PHYSICAL core (what torch picks by default): 128 threads on the 64-core / 128-thread GPU host were
+    # measured 8x slower than 64 (oversubscribed hyper-threads).
     try:
         avail = len(os.sched_getaffinity(0))
     except AttributeError:
         avail = os.cpu_count() or 1
-    torch.set_num_threads(threads or avail)
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False) or avail
+    except Exception:
+        phys = avail
+    torch.set_num_threads(threads or max(1, min(avail, phys)))
     cores = torch.get_num_threads()
     inp = make_config(frames_cfg, seed=1, B=1)
     klist = [float(v) for v in inp.k.tolist()]

@@ -31,6 +31,7 @@ timeout 600 python bench.py --config cfg3 --no-cpu-baseline --steps 100 > "$OUT/
 for v in cells_noreuse window direct; do
   timeout 600 python bench.py --variant $v --no-cpu-baseline --no-gnet --steps 20 --warmup 3 > "$OUT/bench_$v.json" 2>> "$OUT/bench.err"; echo "variant $v" | tee -a "$S"; pick "$OUT/bench_$v.json" | tee -a "$S"
 done
+timeout 600 python scripts/sweep.py "$OUT/sweep.md" > "$OUT/sweep.log" 2>&1; echo "sweep rc=$?" | tee -a "$S"
 for lib in "$@"; do
   MAGNET_B200_LIB=$PWD/magnet_b200/libmagnet_b200_$lib.so timeout 600 python bench.py --no-cpu-baseline --no-gnet --steps 50 --warmup 5 > "$OUT/bench_$lib.json" 2>> "$OUT/bench.err"
   echo "tuning $lib" | tee -a "$S"; pick "$OUT/bench_$lib.json" | tee -a "$S"

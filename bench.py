@@ -312,15 +312,22 @@ def main():
         def gnet_step():
             plan = magnet_b200.MatchingPlan(g.ref_feat, g.nghbr_feat, g.nghbr_gmms, g.nghbr_poses, is_valid_d,
                                             {"intM": intM_d, "unit_ray_array_2D": rays_d}, thres=inp.thres)
-            return magnet_b200.matching_loop(plan, g.ref_gmms, x_d3, head.gnet, N_ITER, karr, variant=variant)[-1]
+            return magnet_b200.matching_loop(plan, g.ref_gmms, x_d3, head if split else head.gnet, N_ITER, karr,
+                                             variant=variant)[-1]
 
+        res = {}
         with torch.no_grad():
-            for _ in range(3):
-                gnet_step()
-            kg = max(3, K // 10)
-            ms_g = timed(gnet_step, kg) / kg
+            for split in (False, True):
+                for _ in range(3):
+                    gnet_step()
+                kg = max(3, K // 10)
+                res[split] = timed(gnet_step, kg) / kg
+        ms_g = res[True]
         with_gnet = {"value": world * B * 1e3 / ms_g, "unit": "frames/s", "ms_per_step": ms_g,
-                     "note": "same loop + G-Net conv head (cuDNN, fp32) on a random 256-ch D-Net feature"}
+                     "reference_dataflow_ms_per_step": res[False],
+                     "note": "same loop + G-Net conv head (cuDNN, fp32) on a random 256-ch D-Net feature; headline = "
+                             "x_d3 half of the first conv hoisted out of the loop (no per-iteration cat), "
+                             "reference_dataflow = cat([cost, x_d3]) every iteration as MAGNET.py:167"}
 
     # ---- e2e: drop-in API, pinned host buffers, H2D + D2H inside the timed region ---------------------------
     host = {k: getattr(inp, k).contiguous().pin_memory() for k in ("ref_feat", "nghbr_feat", "ref_gmms", "nghbr_gmms", "nghbr_poses")}

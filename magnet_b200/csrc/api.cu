@@ -25,21 +25,6 @@ cudaError_t launch_sample(const float* gmm, const float* k_host, int B, int D, i
 cudaError_t launch_update_fwd(const float* dout, const float* gmm0, int B, int HW, float* out, cudaStream_t st);
 cudaError_t launch_update_bwd(const float* gout, const float* dout, const float* gmm0, int B, int HW, float* gin,
                               cudaStream_t st);
-struct BwdParams {
-  int B, V, D, C, H, W, HW;
-  int softmax;
-  float vf;
-  const float* ref_feat;
-  const float* src_feat;
-  const float* rays;
-  const magnet_camera* cams;
-  const float* prob;
-  const float* grad_out;
-  float* g_score;
-  float* grad_ref;
-  float* grad_src;
-  float k[MAGNET_MAX_PLANES];
-};
 cudaError_t launch_cost_f_bwd(const BwdParams& p, cudaStream_t st, int* launches);
 }  // namespace magnet
 
@@ -151,8 +136,8 @@ int magnet_cost_volume_f32(const magnet_cost_args* a, void* stream) {
     if (use_window(a))
       e = magnet::launch_cost_window(p, a->depth_mode, a->C, a->consistency != 0, (cudaStream_t)stream);
     else
-    e = magnet::launch_cost_cells(p, a->depth_mode, a->C, a->consistency != 0,
-                                  a->variant != MAGNET_VARIANT_CELLS_NOREUSE, (cudaStream_t)stream);
+      e = magnet::launch_cost_cells(p, a->depth_mode, a->C, a->consistency != 0,
+                                    a->variant != MAGNET_VARIANT_CELLS_NOREUSE, (cudaStream_t)stream);
     launches = 1;
     if (e == cudaSuccess && a->softmax) {          // homography.py:46, in place on the 1/V-averaged scores
       e = magnet::launch_softmax_planes(a->out, a->B, a->D, a->H * a->W, (cudaStream_t)stream);

@@ -25,6 +25,23 @@ struct CostParams {
   float k[MAGNET_MAX_PLANES];
 };
 
+// Kernel-side arguments of the F-volume backward (magnet_cost_f_bwd_args + the geometry of its forward call).
+struct BwdParams {
+  int B, V, D, C, H, W, HW;
+  int softmax;
+  float vf;
+  const float* __restrict__ ref_feat;   // (B,C,H,W)
+  const float* __restrict__ src_feat;   // (V*B,C,H,W) NCHW
+  const float* __restrict__ rays;
+  const magnet_camera* __restrict__ cams;
+  const float* __restrict__ prob;       // (B,D,H,W) forward output (softmax == 1) or unused
+  const float* __restrict__ grad_out;   // (B,D,H,W)
+  float* __restrict__ g_score;          // (B,D,H,W) workspace
+  float* __restrict__ grad_ref;         // (B,C,H,W), written
+  float* __restrict__ grad_src;         // (V*B,C,H,W), accumulated with atomics (caller zeroes it)
+  float k[MAGNET_MAX_PLANES];
+};
+
 // 1/x to <1 ulp: MUFU.RCP + one Newton step.  x == 0 -> NaN/inf, which the callers'
 // coordinate clamp turns into "out of bounds" (same outcome as the reference's +-10 clamp).
 __device__ __forceinline__ float rcp_nr(float x) {

@@ -13,22 +13,6 @@
 
 namespace magnet {
 
-struct BwdParams {
-  int B, V, D, C, H, W, HW;
-  int softmax;
-  float vf;
-  const float* __restrict__ ref_feat;   // (B,C,H,W)
-  const float* __restrict__ src_feat;   // (V*B,C,H,W) NCHW
-  const float* __restrict__ rays;
-  const magnet_camera* __restrict__ cams;
-  const float* __restrict__ prob;       // (B,D,H,W) forward output (softmax == 1) or unused
-  const float* __restrict__ grad_out;   // (B,D,H,W)
-  float* __restrict__ g_score;          // (B,D,H,W) workspace
-  float* __restrict__ grad_ref;         // (B,C,H,W), written
-  float* __restrict__ grad_src;         // (V*B,C,H,W), accumulated with atomics (caller zeroes it)
-  float k[MAGNET_MAX_PLANES];
-};
-
 __global__ void score_grad_kernel(const __grid_constant__ BwdParams p) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= p.HW) return;

@@ -35,6 +35,23 @@ class GNET(nn.Module):
     def forward(self, cost_volume: torch.Tensor, ref_gmm: torch.Tensor) -> torch.Tensor:
         return ops.gaussian_update(self.gnet(cost_volume), ref_gmm)
 
+    # --- G-Net input assembly without the per-iteration cat ------------------------------------
+    # The reference concatenates [cost_volume (D ch), x_d3 (256 ch)] every iteration (MAGNET.py:167, a 197 MB copy at
+    # config 2) and runs the 3x3 conv over all D+256 channels.  x_d3 does not change across iterations, and a
+    # convolution is linear in its input channels:  conv(cat[cv, x]) = conv(cv, W[:, :D]) + conv(x, W[:, D:]) + b.
+    def invariant_part(self, x_d3: torch.Tensor, n_cost_channels: int) -> torch.Tensor:
+        """conv(x_d3, W[:, D:]) + b of the first layer — computed once per forward."""
+        c0 = self.gnet[0]
+        return nn.functional.conv2d(x_d3, c0.weight[:, n_cost_channels:], c0.bias, padding=1)
+
+    def raw_from_parts(self, cost_volume: torch.Tensor, invariant: torch.Tensor) -> torch.Tensor:
+        """The raw (mu_1, sigma_1) output given the cost volume and the precomputed invariant part."""
+        c0 = self.gnet[0]
+        y = nn.functional.conv2d(cost_volume, c0.weight[:, :cost_volume.shape[1]], None, padding=1) + invariant
+        for layer in list(self.gnet)[1:]:
+            y = layer(y)
+        return y
+
 
 class MatchingPlan:
     """Everything about one batch that does not change across the N_iter iterations, prepared once:
@@ -65,19 +82,23 @@ class MatchingPlan:
 
 
 def matching_loop(plan: MatchingPlan, ref_gmms: torch.Tensor, x_d3: torch.Tensor,
-                  g_net_convs: Callable[[torch.Tensor], torch.Tensor], n_iter: int, k: Sequence[float],
+                  g_net_convs, n_iter: int, k: Sequence[float],
                   variant=_lib.VARIANT_AUTO) -> List[torch.Tensor]:
     """pred_list of MAGNET.py:150-169: [ref_gmms, pred_1, ..., pred_n_iter] at quarter resolution.
 
-    ``g_net_convs`` maps the (B, D+256, H, W) concatenation [cost volume, x_d3] to the raw (B,2,H,W)
-    G-Net output (``GNET.gnet``).  Gradients flow exactly where the reference lets them: through the
-    update into the conv weights, never into the cost volume (MAGNET.py:167 detaches it)."""
+    ``g_net_convs`` is either a callable mapping the (B, D+256, H, W) concatenation [cost volume, x_d3] to the
+    raw (B,2,H,W) G-Net output (``GNET.gnet``, the reference's data flow), or a ``GNET`` module — then the
+    iteration-invariant x_d3 half of the first convolution is computed once and the per-iteration ``cat`` is
+    skipped (f-3).  Gradients flow exactly where the reference lets them: through the update into the conv
+    weights, never into the cost volume (MAGNET.py:167 detaches it)."""
     karr = ops.k_array(k)
     preds = [ref_gmms]
+    split = isinstance(g_net_convs, GNET)
+    inv = g_net_convs.invariant_part(x_d3, len(karr)) if split else None
     for _ in range(n_iter):
         cur = preds[-1].detach()
         cv = plan.cost(cur, karr, variant=variant)
-        raw = g_net_convs(torch.cat([cv, x_d3], dim=1))
+        raw = g_net_convs.raw_from_parts(cv, inv) if split else g_net_convs(torch.cat([cv, x_d3], dim=1))
         preds.append(ops.gaussian_update(raw, cur))
     return preds
 
@@ -110,7 +131,7 @@ class MagnetHead(nn.Module):
 
     def forward(self, ref_feat, nghbr_feat, ref_gmms, nghbr_gmms, x_d3, nghbr_poses, is_valid, cam_intrins):
         plan = MatchingPlan(ref_feat, nghbr_feat, nghbr_gmms, nghbr_poses, is_valid, cam_intrins, thres=self.thres)
-        preds = matching_loop(plan, ref_gmms, x_d3, self.g_net.gnet, self.n_iter, self.k_list)
+        preds = matching_loop(plan, ref_gmms, x_d3, self.g_net, self.n_iter, self.k_list)
         mask = self.mask_head(x_d3)
         return [self.upsample(pr, mask, self.downsample_ratio) for pr in preds[1:]]
 

@@ -266,3 +266,27 @@ def test_f_volume_backward_matches_autograd_of_reference_ops(cuda, seed, shape):
     for a, b, name in ((r1.grad, r2.grad, "ref"), (s1.grad, s2.grad, "src")):
         err = float((a - b).abs().max())
         assert err <= 2e-4 * float(b.abs().max()), (name, err, float(b.abs().max()))
+
+
+def test_gnet_split_equals_cat_dataflow(cuda):
+    """f-3: hoisting the iteration-invariant x_d3 half of G-Net's first convolution out of the loop gives the
+    same predictions (and parameter gradients) as the reference's cat([cost, x_d3]) data flow."""
+    inp = make_inputs(B=2, V=2, D=8, H=24, W=32, C=16, seed=71, depth="smooth").to(cuda)
+    torch.manual_seed(1)
+    head = magnet_b200.GNET(ch_in=8 + 256).to(cuda)
+    x_d3 = torch.randn(2, 256, 24, 32, device=cuda)
+    plan = magnet_b200.MatchingPlan(inp.ref_feat, inp.nghbr_feat, inp.nghbr_gmms, inp.nghbr_poses, inp.is_valid,
+                                    inp.cam_intrins, thres=5)
+    k = magnet_b200.depth_sampling(3, 8)
+    grads = []
+    outs = []
+    for g_arg in (head.gnet, head):
+        head.zero_grad()
+        preds = magnet_b200.matching_loop(plan, inp.ref_gmms, x_d3, g_arg, 3, k)
+        preds[-1].square().mean().backward()
+        outs.append(preds[-1].detach())
+        grads.append(torch.cat([p.grad.reshape(-1) for p in head.parameters()]))
+    scale = float(outs[0].abs().max())
+    d = (outs[0] - outs[1]).abs()
+    assert float(d.median()) <= 1e-5 * scale and float((d > 1e-3 * scale).float().mean()) < 2e-3   # mask flips downstream
+    assert float((grads[0] - grads[1]).abs().max()) <= 2e-3 * float(grads[0].abs().max())

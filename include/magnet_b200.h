@@ -166,6 +166,18 @@ int magnet_gaussian_update_fwd_f32(const float* d_output, const float* ref_gmm, 
 int magnet_gaussian_update_bwd_f32(const float* grad_out, const float* d_output, const float* ref_gmm,
                                    int32_t B, int32_t HW, float* grad_d_output, void* stream);
 
+/*
+ * Learned convex upsampling.  Replaces upsample_depth_via_mask (models/MAGNET.py:15-27): softmax over the 9
+ * neighbours of up_mask (B, 9*k*k, H, W) viewed (B,1,9,k,k,H,W), weighted sum of the zero-padded 3x3
+ * neighbourhood of depth (B,CH,H,W), pixel shuffle -> out (B,CH,k*H,k*W).  CH in {1,2}.
+ */
+int magnet_convex_upsample_fwd_f32(const float* depth, const float* up_mask, int32_t B, int32_t CH, int32_t H,
+                                   int32_t W, int32_t k, float* out, void* stream);
+/* Backward: grad_mask (B,9*k*k,H,W) is written; grad_depth (B,CH,H,W) is ACCUMULATED (caller zeroes it). */
+int magnet_convex_upsample_bwd_f32(const float* grad_out, const float* depth, const float* up_mask, int32_t B,
+                                   int32_t CH, int32_t H, int32_t W, int32_t k, float* grad_depth, float* grad_mask,
+                                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,10 @@ cudaError_t launch_sample(const float* gmm, const float* k_host, int B, int D, i
 cudaError_t launch_update_fwd(const float* dout, const float* gmm0, int B, int HW, float* out, cudaStream_t st);
 cudaError_t launch_update_bwd(const float* gout, const float* dout, const float* gmm0, int B, int HW, float* gin,
                               cudaStream_t st);
+cudaError_t launch_upsample_fwd(const float* depth, const float* mask, int B, int CH, int H, int W, int k, float* out,
+                                cudaStream_t st);
+cudaError_t launch_upsample_bwd(const float* gout, const float* depth, const float* mask, int B, int CH, int H, int W,
+                                int k, float* gdepth, float* gmask, cudaStream_t st);
 cudaError_t launch_cost_f_bwd(const BwdParams& p, cudaStream_t st, int* launches);
 }  // namespace magnet
 
@@ -228,6 +232,30 @@ int magnet_gaussian_update_bwd_f32(const float* grad_out, const float* d_output,
   if (!grad_out || !d_output || !ref_gmm || !grad_d_output) return MAGNET_ERR_NULL;
   if (B <= 0 || HW <= 0 || B > 65535) return MAGNET_ERR_SHAPE;
   cudaError_t e = magnet::launch_update_bwd(grad_out, d_output, ref_gmm, B, HW, grad_d_output, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e);
+  g_launches += 1;
+  return MAGNET_OK;
+}
+
+int magnet_convex_upsample_fwd_f32(const float* depth, const float* up_mask, int32_t B, int32_t CH, int32_t H,
+                                   int32_t W, int32_t k, float* out, void* stream) {
+  if (!depth || !up_mask || !out) return MAGNET_ERR_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || k <= 0 || B > 65535 || H * k > 65535) return MAGNET_ERR_SHAPE;
+  if (CH != 1 && CH != 2) return MAGNET_ERR_UNSUPPORTED;
+  cudaError_t e = magnet::launch_upsample_fwd(depth, up_mask, B, CH, H, W, k, out, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e);
+  g_launches += 1;
+  return MAGNET_OK;
+}
+
+int magnet_convex_upsample_bwd_f32(const float* grad_out, const float* depth, const float* up_mask, int32_t B,
+                                   int32_t CH, int32_t H, int32_t W, int32_t k, float* grad_depth, float* grad_mask,
+                                   void* stream) {
+  if (!grad_out || !depth || !up_mask || !grad_depth || !grad_mask) return MAGNET_ERR_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || k <= 0 || B > 65535 || H * k > 65535) return MAGNET_ERR_SHAPE;
+  if (CH != 1 && CH != 2) return MAGNET_ERR_UNSUPPORTED;
+  cudaError_t e = magnet::launch_upsample_bwd(grad_out, depth, up_mask, B, CH, H, W, k, grad_depth, grad_mask,
+                                              (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e);
   g_launches += 1;
   return MAGNET_OK;

@@ -94,6 +94,100 @@ __global__ void gaussian_update_bwd_kernel(const float* __restrict__ gout, const
   gin[(b * 2 + 1) * HW + n] = __fmul_rn(__fmul_rn(g_sg, delu), s0);
 }
 
+// Learned convex upsampling (upsample_depth_via_mask, MAGNET.py:15-27) without the (B,C,9,k,k,H,W) temporaries.
+// One thread per output pixel (b, Y = y*k+ky, X = x*k+kx), all channels: softmax over the 9 mask logits
+// mask[b, (i*k+ky)*k+kx, y, x], weighted sum of the zero-padded 3x3 neighbourhood of depth[b, c, y, x].
+template <int CH>
+__global__ void convex_upsample_fwd_kernel(const float* __restrict__ depth, const float* __restrict__ mask, int H,
+                                           int W, int k, float* __restrict__ out) {
+  const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y;
+  const size_t b = blockIdx.z;
+  if (X >= W * k) return;
+  const int x = X / k, kx = X % k, y = Y / k, ky = Y % k;
+  const size_t HW = (size_t)H * W;
+  const float* mp = mask + (b * 9 * k * k + (size_t)ky * k + kx) * HW + (size_t)y * W + x;
+  float w[9], m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { w[i] = mp[(size_t)i * k * k * HW]; m = fmaxf(m, w[i]); }
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { w[i] = expf(w[i] - m); s += w[i]; }
+  const float inv = 1.0f / s;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const float* dp = depth + (b * CH + c) * HW;
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const int yy = y + i / 3 - 1, xx = x + i % 3 - 1;
+      const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? dp[(size_t)yy * W + xx] : 0.0f;
+      acc = __fmaf_rn(w[i] * inv, v, acc);
+    }
+    out[((b * CH + c) * H * k + Y) * (size_t)(W * k) + X] = acc;
+  }
+}
+
+// Backward of the above w.r.t. the mask logits (softmax backward, written) and the low-resolution map
+// (scatter-add with red.add into grad_depth, which the caller zeroes).
+template <int CH>
+__global__ void convex_upsample_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ depth,
+                                           const float* __restrict__ mask, int H, int W, int k,
+                                           float* __restrict__ gdepth, float* __restrict__ gmask) {
+  const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y;
+  const size_t b = blockIdx.z;
+  if (X >= W * k) return;
+  const int x = X / k, kx = X % k, y = Y / k, ky = Y % k;
+  const size_t HW = (size_t)H * W;
+  const size_t moff = (b * 9 * k * k + (size_t)ky * k + kx) * HW + (size_t)y * W + x;
+  float w[9], m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { w[i] = mask[moff + (size_t)i * k * k * HW]; m = fmaxf(m, w[i]); }
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { w[i] = expf(w[i] - m); s += w[i]; }
+  const float inv = 1.0f / s;
+  float t[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { w[i] *= inv; t[i] = 0.0f; }
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const float g = gout[((b * CH + c) * H * k + Y) * (size_t)(W * k) + X];
+    const float* dp = depth + (b * CH + c) * HW;
+    float* gd = gdepth + (b * CH + c) * HW;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const int yy = y + i / 3 - 1, xx = x + i % 3 - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        t[i] = __fmaf_rn(g, dp[(size_t)yy * W + xx], t[i]);
+        atomicAdd(gd + (size_t)yy * W + xx, g * w[i]);
+      }
+    }
+  }
+  float dot = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) dot = __fmaf_rn(w[i], t[i], dot);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) gmask[moff + (size_t)i * k * k * HW] = w[i] * (t[i] - dot);
+}
+
+cudaError_t launch_upsample_fwd(const float* depth, const float* mask, int B, int CH, int H, int W, int k, float* out,
+                                cudaStream_t st) {
+  dim3 grid((W * k + 127) / 128, H * k, B);
+  if (CH == 1) convex_upsample_fwd_kernel<1><<<grid, 128, 0, st>>>(depth, mask, H, W, k, out);
+  else if (CH == 2) convex_upsample_fwd_kernel<2><<<grid, 128, 0, st>>>(depth, mask, H, W, k, out);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_upsample_bwd(const float* gout, const float* depth, const float* mask, int B, int CH, int H, int W,
+                                int k, float* gdepth, float* gmask, cudaStream_t st) {
+  dim3 grid((W * k + 127) / 128, H * k, B);
+  if (CH == 1) convex_upsample_bwd_kernel<1><<<grid, 128, 0, st>>>(gout, depth, mask, H, W, k, gdepth, gmask);
+  else if (CH == 2) convex_upsample_bwd_kernel<2><<<grid, 128, 0, st>>>(gout, depth, mask, H, W, k, gdepth, gmask);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_pack_cameras(const float* intM, const float* R, int64_t r_sb, int64_t r_sv, int64_t r_si,
                                 int64_t r_sj, const float* t, int64_t t_sb, int64_t t_sv, int64_t t_si,
                                 const int32_t* is_valid, int B, int V, magnet_camera* out, cudaStream_t st) {

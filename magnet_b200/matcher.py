@@ -124,10 +124,8 @@ class MagnetHead(nn.Module):
 
     @staticmethod
     def upsample(depth, up_mask, k):
-        N, o_dim, H, W = depth.shape
-        m = torch.softmax(up_mask.view(N, 1, 9, k, k, H, W), dim=2)
-        nb = nn.functional.unfold(depth, [3, 3], padding=1).view(N, o_dim, 9, 1, 1, H, W)
-        return torch.sum(m * nb, dim=2).permute(0, 1, 4, 2, 5, 3).reshape(N, o_dim, k * H, k * W)
+        """upsample_depth_via_mask (MAGNET.py:15-27) — fused kernels, no (B,2,9,k,k,H,W) temporaries (f-2)."""
+        return ops.convex_upsample(depth, up_mask, k)
 
     def forward(self, ref_feat, nghbr_feat, ref_gmms, nghbr_gmms, x_d3, nghbr_poses, is_valid, cam_intrins):
         plan = MatchingPlan(ref_feat, nghbr_feat, nghbr_gmms, nghbr_poses, is_valid, cam_intrins, thres=self.thres)

@@ -199,3 +199,37 @@ class GaussianUpdate(torch.autograd.Function):
 
 def gaussian_update(d_output: torch.Tensor, ref_gmm: torch.Tensor) -> torch.Tensor:
     return GaussianUpdate.apply(d_output, ref_gmm)
+
+
+class ConvexUpsample(torch.autograd.Function):
+    """upsample_depth_via_mask (MAGNET.py:15-27) as one kernel each way; differentiable in depth and mask."""
+
+    @staticmethod
+    def forward(ctx, depth: torch.Tensor, up_mask: torch.Tensor, k: int) -> torch.Tensor:
+        depth = _need_cuda_f32("depth", depth)
+        up_mask = _need_cuda_f32("up_mask", up_mask)
+        B, CH, H, W = depth.shape
+        if up_mask.shape != (B, 9 * k * k, H, W):
+            raise _lib.MagnetError(f"up_mask must be (B, 9*k*k, H, W) = {(B, 9 * k * k, H, W)}, got {tuple(up_mask.shape)}")
+        out = torch.empty(B, CH, k * H, k * W, device=depth.device, dtype=torch.float32)
+        check(lib().magnet_convex_upsample_fwd_f32(depth.data_ptr(), up_mask.data_ptr(), B, CH, H, W, k, out.data_ptr(),
+                                                   _stream()), "magnet_convex_upsample_fwd_f32")
+        ctx.save_for_backward(depth, up_mask)
+        ctx.k = k
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: torch.Tensor):
+        depth, up_mask = ctx.saved_tensors
+        grad_out = _need_cuda_f32("grad_out", grad_out)
+        B, CH, H, W = depth.shape
+        g_depth = torch.zeros_like(depth)
+        g_mask = torch.empty_like(up_mask)
+        check(lib().magnet_convex_upsample_bwd_f32(grad_out.data_ptr(), depth.data_ptr(), up_mask.data_ptr(), B, CH, H, W,
+                                                   ctx.k, g_depth.data_ptr(), g_mask.data_ptr(), _stream()),
+              "magnet_convex_upsample_bwd_f32")
+        return g_depth, g_mask, None
+
+
+def convex_upsample(depth: torch.Tensor, up_mask: torch.Tensor, k: int) -> torch.Tensor:
+    return ConvexUpsample.apply(depth, up_mask, k)

@@ -290,3 +290,21 @@ def test_gnet_split_equals_cat_dataflow(cuda):
     d = (outs[0] - outs[1]).abs()
     assert float(d.median()) <= 1e-5 * scale and float((d > 1e-3 * scale).float().mean()) < 2e-3   # mask flips downstream
     assert float((grads[0] - grads[1]).abs().max()) <= 2e-3 * float(grads[0].abs().max())
+
+
+def test_convex_upsample_kernels_vs_reference(cuda):
+    """f-2: fused convex upsampling against the reference's own output (golden) and, for the backward, against
+    autograd through the ATen port of upsample_depth_via_mask."""
+    from oracle import torch_ref
+    z, _ = load_golden("update_upsample")
+    depth = torch.from_numpy(z["depth"]).to(cuda).requires_grad_(True)
+    mask = torch.from_numpy(z["mask"]).to(cuda).requires_grad_(True)
+    up = ops.convex_upsample(depth, mask, 4)
+    assert np.allclose(up.detach().cpu().numpy(), z["up"], rtol=1e-5, atol=1e-6)
+    g = torch.randn_like(up)
+    (up * g).sum().backward()
+    d2 = torch.from_numpy(z["depth"]).to(cuda).requires_grad_(True)
+    m2 = torch.from_numpy(z["mask"]).to(cuda).requires_grad_(True)
+    (torch_ref.convex_upsample(d2, m2, 4) * g).sum().backward()
+    assert float((depth.grad - d2.grad).abs().max()) <= 1e-5 * float(d2.grad.abs().max())
+    assert float((mask.grad - m2.grad).abs().max()) <= 1e-5 * float(m2.grad.abs().max())

@@ -8,24 +8,25 @@
 // distinct cell needs 4 channel dot products <ref[p], src[tap]> (plus 4 taps of source mu and
 // sigma); every hypothesis inside the cell is then a 3-FMA bilinear polynomial per quantity.
 //
-// Mapping: one thread per reference pixel (a warp = 32 consecutive pixels of a row, so source
-// gathers of neighbouring lanes hit neighbouring addresses), loops over hypothesis chunks and views
-// inside the thread.  Per (pixel, chunk, view) the work is split into three phases that every lane
-// of a warp executes in LOCKSTEP — a run-per-cell loop would diverge 2.2x on the bench workload
-// (measured by simulation):
-//   A  walk the hypotheses j in order, record every change of bilinear cell -> per-lane cell list
-//      (headers in shared memory, at most NCELL per round);
-//   B  for cell i = 0..warp-max: channel dot products + mu/sigma taps of the taps that are NEW with
-//      respect to the lane's previous cell (an edge-adjacent cell shares two taps, kept in
-//      registers) -> 12 polynomial coefficients per cell, 3 float4 per lane in shared memory;
-//   C  walk the hypotheses again; on leaving the current cell reload the next record (3 LDS.128,
-//      the only divergent code), evaluate cost / mu~ / sigma~, apply the consistency test and
-//      accumulate over views in a shared-memory column owned by the lane.
-// If a lane needs more than NCELL cells (incoherent depth, e.g. random test inputs) the warp
-// processes the hypotheses in several rounds [j_lo, j_end), j_end = warp-min of the first
-// hypothesis a lane could not record — always correct, no separate slow path.
-// Hypotheses are accumulated in chunks of JCHUNK so the accumulator column stays small
-// (16 KB per CTA) and 4 CTAs (16 warps) fit per SM; the softmax variant keeps all D planes.
+// Mapping: one thread per reference pixel; a CTA is a 16x8 pixel tile (a warp = 2 rows x 16 pixels, so the
+// gathers of neighbouring lanes hit neighbouring addresses and the CTA's source footprint stays compact)
+// and owns ONE chunk of JCHUNK = 32 hypotheses (the chunks of a tile are adjacent CTAs).  Per view the work is
+// split into three phases that every lane of a warp executes in LOCKSTEP — a run-per-cell loop would diverge
+// 2.2x on the bench workload (measured by simulation):
+//   A  cell list: analytic walk from grid line to grid line in depth space + binary search for the first
+//      hypothesis of each cell (cells_common.cuh: cell_list); exact per-hypothesis walk as the fallback
+//      (d_volume mode, points behind the camera, unsorted k).  Headers in shared memory, at most NCELL per
+//      round, plus a bit mask of the hypotheses that start a cell;
+//   B  for cell i = 0..warp-max: channel dot products + mu/sigma of the taps that are NEW with respect to
+//      the lane's previous cell (an edge-adjacent cell shares two taps, kept in registers), loads clamped
+//      instead of predicated and batched (16 LDG.128 in flight) -> 12 polynomial coefficients per cell,
+//      3 float4 per lane in shared memory;
+//   C  walk the hypotheses; where the mask says a cell starts reload the record (3 LDS.128, the only
+//      divergent code), evaluate cost / mu~ / sigma~, apply the consistency test and accumulate over views
+//      in a shared-memory column owned by the lane.
+// If a lane needs more than NCELL cells (incoherent depth, e.g. random test inputs) the warp processes the
+// hypotheses in several rounds [j_lo, j_end), j_end = warp-min of the first hypothesis a lane could not
+// cover — always correct, no separate slow path.  52 KB shared memory and 168 registers -> 3 CTAs per SM.
 //
 // Source features are gathered from the TILED32 layout (N, H, W/32, C/4, 32, 4): the 16 channel
 // quads of one pixel sit at a compile-time stride (512 B), so one base address + immediates serve
@@ -59,7 +60,7 @@ constexpr int NT = 128;                // threads per CTA = reference pixels per
 constexpr int TILE_W = MAGNET_TILE_W;  // CTA tile = TILE_W x (NT / TILE_W) reference pixels (2-D keeps the
 constexpr int TILE_H = NT / TILE_W;    // source footprint of a CTA compact enough for L1 to capture tap reuse)
 constexpr int NCELL = MAGNET_NCELL;    // cell records per lane per round
-constexpr int JCHUNK = MAGNET_JCHUNK;  // hypotheses per accumulation chunk (non-softmax variants)
+constexpr int JCHUNK = MAGNET_JCHUNK;  // hypotheses per CTA (accumulation chunk)
 
 __host__ __device__ inline int cells_chunk(int D) { return D < JCHUNK ? D : JCHUNK; }
 // dynamic shared memory: rec[NCELL][3][NT] float4 | hdr[NCELL][NT] float2 | acc[chunk][NT] float | ks[chunk]

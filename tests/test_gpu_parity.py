@@ -57,6 +57,9 @@ def test_cw_known_answers_gpu(cuda, case, vname, variant):
     (22, "smooth", dict(B=1, V=4, D=64, H=30, W=40, C=64)),
     (23, "random", dict(B=1, V=1, D=33, H=9, W=50, C=32)),       # > NCELL cells per lane -> several rounds
     (24, "smooth", dict(B=3, V=3, D=16, H=12, W=12, C=20)),      # C not instantiated by the cells kernel -> direct
+    (25, "smooth", dict(B=1, V=2, D=5, H=30, W=40, C=64)),       # the reference's shipped N_s = 5 (one partial chunk)
+    (26, "smooth", dict(B=1, V=2, D=80, H=10, W=24, C=32)),      # 2.5 chunks
+    (27, "smooth", dict(B=1, V=1, D=256, H=6, W=20, C=16)),      # MAGNET_MAX_PLANES
 ])
 def test_cw_vs_oracle_seeded(cuda, seed, depth, shape):
     inp = make_inputs(seed=seed, depth=depth, invalid=[(0, 0)] if shape["V"] > 1 else (), **shape)
@@ -308,3 +311,21 @@ def test_convex_upsample_kernels_vs_reference(cuda):
     (torch_ref.convex_upsample(d2, m2, 4) * g).sum().backward()
     assert float((depth.grad - d2.grad).abs().max()) <= 1e-5 * float(d2.grad.abs().max())
     assert float((mask.grad - m2.grad).abs().max()) <= 1e-5 * float(m2.grad.abs().max())
+
+
+@pytest.mark.parametrize("vname,variant", VARIANTS)
+def test_points_behind_the_source_camera(cuda, vname, variant):
+    """The reference has no positive-depth test: hypotheses behind a source camera are projected and
+    sampled like any other.  A source view translated 3 m forward puts about half of them behind it; the analytic
+    cell walk must hand those lanes to the exact walk, and the result must still match the oracle."""
+    inp = make_inputs(B=1, V=2, D=32, H=16, W=24, C=16, seed=81, depth="smooth")
+    inp.nghbr_poses[0, 0, 2, 3] = -3.0            # z_src = z_ref - 3 < 0 for depths below 3 m
+    inp.nghbr_poses[0, 1, 2, 3] = -2.4
+    dvol = inp.depth_volume()
+    want, margin = oracle_cw(inp, dvol.numpy(), return_margin=True)
+    g = inp.to(cuda)
+    plan = magnet_b200.MatchingPlan(g.ref_feat, g.nghbr_feat, g.nghbr_gmms, g.nghbr_poses, inp.is_valid,
+                                    inp.cam_intrins, thres=5)
+    fused = plan.cost(g.ref_gmms, inp.k.tolist(), variant=variant).cpu().numpy()
+    compare_volume(fused, want, margin, what=f"behind/{vname}/fused")
+    compare_volume(_run_cw(inp, dvol, cuda, variant), want, margin, what=f"behind/{vname}/drop-in")

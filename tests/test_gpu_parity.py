@@ -334,3 +334,41 @@ def test_points_behind_the_source_camera(cuda, vname, variant):
     fused = plan.cost(g.ref_gmms, inp.k.tolist(), variant=variant).cpu().numpy()
     compare_volume(fused, want, margin, what=f"behind/{vname}/fused")
     compare_volume(_run_cw(inp, dvol, cuda, variant), want, margin, what=f"behind/{vname}/drop-in")
+
+
+def test_iteration_is_cuda_graph_capturable(cuda):
+    """include/magnet_b200.h promises: no allocation, no synchronisation, every launch on the given stream.  So one
+    matching iteration (fused cost kernel + update kernel) must capture into a CUDA graph and replay bit-identically."""
+    inp = make_inputs(B=2, V=2, D=16, H=24, W=32, C=32, seed=91, depth="smooth").to(cuda)
+    plan = magnet_b200.MatchingPlan(inp.ref_feat, inp.nghbr_feat, inp.nghbr_gmms, inp.nghbr_poses, inp.is_valid,
+                                    inp.cam_intrins, thres=5)
+    k = ops.k_array(inp.k.tolist())
+    raw = torch.randn(2, 2, 24, 32, device=cuda) * 0.1
+    cv = torch.empty(2, 16, 24, 32, device=cuda)
+    gmm_in = inp.ref_gmms.clone()
+    gmm_out = torch.empty_like(gmm_in)
+
+    def iteration():
+        plan.cost(gmm_in, k, out=cv)
+        gmm_out.copy_(ops.gaussian_update(raw, gmm_in))
+
+    iteration()                                   # warm-up outside capture (one-time function attributes)
+    torch.cuda.synchronize()
+    eager_cv, eager_gmm = cv.clone(), gmm_out.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            iteration()
+    torch.cuda.current_stream().wait_stream(side)
+    cv.zero_()
+    gmm_out.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(cv, eager_cv) and torch.equal(gmm_out, eager_gmm)
+    gmm_in.mul_(1.05)                             # new inputs in the same buffers, replay again
+    graph.replay()
+    torch.cuda.synchronize()
+    want = plan.cost(gmm_in, k)
+    assert torch.equal(cv, want)

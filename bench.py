@@ -416,6 +416,49 @@ def main():
                 "traffic": ncu_traffic(args.config), "kernel": "cost_cells_kernel<64,GAUSS,CW> (TILED32 gather)" if variant != _lib.VARIANT_DIRECT else "cost_direct_kernel<CW>",
                 "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src,
                 "launch": {"grid": grid, "block": block, "smem_bytes": smem}}
+    # ---- reference-CUDA baseline (north_star / BASELINE.md §2): the reference's operator sequence (repeat,
+    # grid_sample, mul, sum ... — ATen port, bit-identical to the reference on CPU) on the same B200, same inputs
+    reference_cuda = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import torch_ref
+        torch.backends.cuda.matmul.allow_tf32 = False
+        dvol_ref = ops.sample_depths(g.ref_gmms, karr)
+        cam_dev = {"intM": intM_d, "unit_ray_array_2D": rays_d}
+
+        def ref_call():
+            return torch_ref.cost_volume_cw(dvol_ref, g.ref_feat, g.nghbr_feat, g.ref_gmms, g.nghbr_gmms, g.R, g.t,
+                                            inp.is_valid, cam_dev, inp.thres)
+
+        with torch.no_grad():
+            ref_out = ref_call()
+            ours_out = magnet_b200.est_costvolume_CW(dvol_ref, g.ref_feat, g.nghbr_feat, g.ref_gmms, g.nghbr_gmms, g.R,
+                                                     g.t, inp.is_valid, inp.cam_intrins, inp.thres)
+            scale = float(ref_out.abs().max())
+            frac_diff = float(((ours_out - ref_out).abs() > 1e-4 * scale).float().mean())
+            torch.cuda.synchronize()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            for _ in range(3):
+                ref_call()
+            r1.record()
+            torch.cuda.synchronize()
+            o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            o0.record()
+            for _ in range(10):
+                magnet_b200.est_costvolume_CW(dvol_ref, g.ref_feat, g.nghbr_feat, g.ref_gmms, g.nghbr_gmms, g.R, g.t,
+                                              inp.is_valid, inp.cam_intrins, inp.thres)
+            o1.record()
+            torch.cuda.synchronize()
+        ms_ref = r0.elapsed_time(r1) / 3
+        reference_cuda = {"ms_per_cost_volume": ms_ref, "frames_per_s_cost_only": B * 1e3 / (N_ITER * ms_ref),
+                          "ours_ms_per_cost_volume_drop_in": o0.elapsed_time(o1) / 10,
+                          "frac_elements_beyond_1e-4": frac_diff,
+                          "note": "est_costvolume_CW operator sequence of the reference on CUDA tensors (stock ATen "
+                                  "grid_sample / repeat / elementwise kernels), same B=%d batch; frames/s counts %d such "
+                                  "calls per frame and nothing else" % (B, N_ITER)}
+        del ref_out, ours_out
+        torch.cuda.empty_cache()
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         fps, info = cpu_reference_frames(args.config, steps=8, warmup=1, budget_s=20.0)
@@ -430,7 +473,7 @@ def main():
                    "step": "repack + camera table + %d x (fused cost kernel + update kernel)" % N_ITER},
         "clocks": sampler.report() if sampler else None,
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "with_gnet": with_gnet,
+        "reference_cuda": reference_cuda, "with_gnet": with_gnet,
     }
     print(json.dumps(line), flush=True)
     md.shutdown()

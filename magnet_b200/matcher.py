@@ -134,6 +134,48 @@ class MagnetHead(nn.Module):
         return [self.upsample(pr, mask, self.downsample_ratio) for pr in preds[1:]]
 
 
+class MAGNET(nn.Module):
+    """The reference's ``MAGNET`` (models/MAGNET.py:73-175) with the matching loop on the B200 kernels.
+
+    Same forward signature and return value: ``forward(ref_img, nghbr_imgs, nghbr_poses, is_valid, cam_intrins,
+    mode)`` -> list of N_iter upsampled (B,2,H,W) Gaussians.  The backbones are passed in (the reference builds
+    them from checkpoints / torch.hub, out of scope here): ``d_net(imgs) -> ((N,2,h,w) [mu, sigma], (N,256,h,w))``
+    and ``f_net(imgs) -> (N,C,h,w)`` as DNET.py:62-67 / F_psmnet.py:122-124; they are frozen and run under
+    ``no_grad`` in ``eval()`` mode exactly like MAGNET.py:82-92,133-144.  ``g_net`` / ``mask_head`` have the
+    reference's parameter names, so ``load_state_dict`` of a reference checkpoint's head works."""
+
+    def __init__(self, d_net: nn.Module, f_net: nn.Module, n_samples: int = 5, sampling_range: float = 3,
+                 weighting: str = "CW5", train_iter: int = 3, test_iter: int = 3, downsample_ratio: int = 4,
+                 dnet_fdim: int = 256):
+        super().__init__()
+        self.d_net, self.f_net = d_net, f_net
+        for net in (self.d_net, self.f_net):
+            for prm in net.parameters():
+                prm.requires_grad = False
+            net.eval()
+        self.train_iter, self.test_iter = train_iter, test_iter
+        thres = int(weighting.split('CW')[1])                   # "CW5" -> kappa = 5 (MAGNET.py:159)
+        self.head = MagnetHead(n_samples=n_samples, sampling_range=sampling_range, n_iter=train_iter, thres=thres,
+                               downsample_ratio=downsample_ratio, dnet_fdim=dnet_fdim)
+        self.g_net, self.mask_head = self.head.g_net, self.head.mask_head   # reference attribute names
+
+    def train(self, mode: bool = True):
+        super().train(mode)
+        self.d_net.eval()        # frozen backbones stay in eval (the reference's model.train() flips them — SURVEY §2.3 quirk)
+        self.f_net.eval()
+        return self
+
+    def forward(self, ref_img, nghbr_imgs, nghbr_poses, is_valid, cam_intrins, mode='train'):
+        B = ref_img.shape[0]
+        with torch.no_grad():
+            imgs = torch.cat((ref_img, nghbr_imgs), dim=0)
+            mono_gmms, x_d3 = self.d_net(imgs)
+            feat = self.f_net(imgs)
+        self.head.n_iter = self.train_iter if mode == 'train' else self.test_iter
+        return self.head(feat[:B], feat[B:], mono_gmms[:B].detach(), mono_gmms[B:].detach(), x_d3[:B], nghbr_poses,
+                         is_valid, cam_intrins)
+
+
 def install(homography_module=None) -> None:
     """Rebind the reference's operators to the B200 kernels so that ``MAGNET.forward`` /
     ``MAGNET_F.forward`` / ``test_MaGNet.py`` run unchanged:

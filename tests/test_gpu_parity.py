@@ -372,3 +372,52 @@ def test_iteration_is_cuda_graph_capturable(cuda):
     torch.cuda.synchronize()
     want = plan.cost(gmm_in, k)
     assert torch.equal(cv, want)
+
+
+def test_magnet_module_matches_reference_dataflow(cuda):
+    """magnet_b200.MAGNET (reference forward signature, backbones injected) against the reference data flow
+    (MAGNET.py:130-175) assembled from the ATen port on the same device, with small stand-in backbones."""
+    import torch.nn as nn
+    from oracle import torch_ref
+
+    class TinyD(nn.Module):                     # (N,3,H,W) -> ((N,2,H/4,W/4) [mu, sigma>0], (N,256,H/4,W/4))
+        def __init__(self):
+            super().__init__()
+            self.a, self.b = nn.Conv2d(3, 2, 4, stride=4), nn.Conv2d(3, 256, 4, stride=4)
+
+        def forward(self, x):
+            g = self.a(x)
+            return torch.cat([2.5 + 0.5 * torch.tanh(g[:, :1]), 0.2 + 0.05 * torch.sigmoid(g[:, 1:])], 1), self.b(x)
+
+    class TinyF(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.c = nn.Conv2d(3, 16, 4, stride=4)
+
+        def forward(self, x):
+            return self.c(x)
+
+    torch.manual_seed(3)
+    B, V, H, W = 2, 2, 96, 128
+    inp = make_inputs(B=B, V=V, D=8, H=H // 4, W=W // 4, C=16, seed=95, depth="smooth")
+    model = magnet_b200.MAGNET(TinyD(), TinyF(), n_samples=8, weighting="CW5", test_iter=2).to(cuda).eval()
+    ref_img = torch.rand(B, 3, H, W, device=cuda)
+    nghbr_imgs = torch.rand(V * B, 3, H, W, device=cuda)
+    poses = inp.nghbr_poses.to(cuda)
+    with torch.no_grad():
+        ours = model(ref_img, nghbr_imgs, poses, inp.is_valid, inp.cam_intrins, mode='test')
+        # reference data flow on the same tensors
+        gm, x_d3 = model.d_net(torch.cat((ref_img, nghbr_imgs), 0))
+        feat = model.f_net(torch.cat((ref_img, nghbr_imgs), 0))
+        holder = type("H", (), {})()
+        holder.ref_feat, holder.nghbr_feat, holder.ref_gmms, holder.nghbr_gmms = feat[:B], feat[B:], gm[:B], gm[B:]
+        holder.R, holder.t = poses[:, :, :3, :3], poses[:, :, :3, 3]
+        holder.is_valid, holder.cam_intrins = inp.is_valid, {k: v.to(cuda) for k, v in inp.cam_intrins.items()}
+        preds = torch_ref.matching_iterations(holder, model.g_net.gnet, x_d3[:B], 2, model.head.k_list, 5)
+        mask = model.mask_head(x_d3[:B])
+        theirs = [torch_ref.convex_upsample(pr, mask, 4) for pr in preds[1:]]
+    assert len(ours) == len(theirs) == 2 and ours[0].shape == (B, 2, H, W)
+    for a, b in zip(ours, theirs):
+        d = (a - b).abs()
+        assert float(d.median()) <= 1e-5 * float(b.abs().max())
+        assert float((d > 1e-3 * float(b.abs().max())).float().mean()) < 2e-3     # downstream of rare mask flips

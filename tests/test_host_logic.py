@@ -135,3 +135,21 @@ def test_synthetic_conventions():
     assert inp.nghbr_feat.shape[0] == 6 and inp.is_valid.dtype == torch.int32 and not inp.is_valid.is_cuda
     assert int(inp.is_valid[1, 0]) == 0 and inp.R.shape == (2, 3, 3, 3) and not inp.R.is_contiguous()
     assert inp.depth_volume().shape == (2, 5, 8, 8)
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under magnet_b200/ (or the C sources) may import, call or link it."""
+    pkg = os.path.join(ROOT, "magnet_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", text, re.M) or "oracle/" in text or "torch_ref" in text:
+                    offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders
+    # and the only top-level users are the allowed ones
+    allowed = {"bench.py", "__graft_entry__.py"}
+    for f in os.listdir(ROOT):
+        if f.endswith(".py") and f not in allowed:
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", open(os.path.join(ROOT, f)).read(), re.M), f

@@ -167,6 +167,23 @@ int magnet_gaussian_update_bwd_f32(const float* grad_out, const float* d_output,
                                    int32_t B, int32_t HW, float* grad_d_output, void* stream);
 
 /*
+ * Caller-side camera preparation on the device.
+ * magnet_relative_poses_f32 replaces utils/utils.py:72-98 (data_preprocess): poses_out[b,v] = ext_nghbr[v,b] *
+ * inv(ext_ref[b]) (ref-camera -> source-camera), is_valid_out[b,v] = 0 when either extrinsic or the product holds a
+ * NaN (the pose is then all zeros).  ext_ref (B,4,4); ext_nghbr (V,B,4,4) view-major; poses_out (B,V,4,4).
+ */
+int magnet_relative_poses_f32(const float* ext_ref, const float* ext_nghbr, int32_t B, int32_t V, float* poses_out,
+                              int32_t* is_valid_out, void* stream);
+/*
+ * magnet_camera_rays_f32 replaces get_ray_array + get_cam_intrinsics (data/dataloader_scannet.py:113-153):
+ * raw_intrinsics (B,6) float64 on the device = fx, fy, cx, cy of the raw image and its width, height;
+ * intM_out (B,3,3) = intrinsics scaled to the H x W grid; rays_out (B,3,H*W) = K_raw^-1 (pixel centre), z = 1.
+ * Evaluated in fp64 and rounded once, bit-identical to the numpy original.
+ */
+int magnet_camera_rays_f32(const double* raw_intrinsics, int32_t B, int32_t H, int32_t W, float* intM_out,
+                           float* rays_out, void* stream);
+
+/*
  * Learned convex upsampling.  Replaces upsample_depth_via_mask (models/MAGNET.py:15-27): softmax over the 9
  * neighbours of up_mask (B, 9*k*k, H, W) viewed (B,1,9,k,k,H,W), weighted sum of the zero-padded 3x3
  * neighbourhood of depth (B,CH,H,W), pixel shuffle -> out (B,CH,k*H,k*W).  CH in {1,2}.

@@ -25,6 +25,9 @@ cudaError_t launch_sample(const float* gmm, const float* k_host, int B, int D, i
 cudaError_t launch_update_fwd(const float* dout, const float* gmm0, int B, int HW, float* out, cudaStream_t st);
 cudaError_t launch_update_bwd(const float* gout, const float* dout, const float* gmm0, int B, int HW, float* gin,
                               cudaStream_t st);
+cudaError_t launch_relative_poses(const float* ext_ref, const float* ext_nghbr, int B, int V, float* poses,
+                                  int32_t* valid, cudaStream_t st);
+cudaError_t launch_camera_rays(const double* raw, int B, int H, int W, float* intM, float* rays, cudaStream_t st);
 cudaError_t launch_upsample_fwd(const float* depth, const float* mask, int B, int CH, int H, int W, int k, float* out,
                                 cudaStream_t st);
 cudaError_t launch_upsample_bwd(const float* gout, const float* depth, const float* mask, int B, int CH, int H, int W,
@@ -232,6 +235,26 @@ int magnet_gaussian_update_bwd_f32(const float* grad_out, const float* d_output,
   if (!grad_out || !d_output || !ref_gmm || !grad_d_output) return MAGNET_ERR_NULL;
   if (B <= 0 || HW <= 0 || B > 65535) return MAGNET_ERR_SHAPE;
   cudaError_t e = magnet::launch_update_bwd(grad_out, d_output, ref_gmm, B, HW, grad_d_output, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e);
+  g_launches += 1;
+  return MAGNET_OK;
+}
+
+int magnet_relative_poses_f32(const float* ext_ref, const float* ext_nghbr, int32_t B, int32_t V, float* poses_out,
+                              int32_t* is_valid_out, void* stream) {
+  if (!ext_ref || !ext_nghbr || !poses_out || !is_valid_out) return MAGNET_ERR_NULL;
+  if (B <= 0 || V <= 0) return MAGNET_ERR_SHAPE;
+  cudaError_t e = magnet::launch_relative_poses(ext_ref, ext_nghbr, B, V, poses_out, is_valid_out, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e);
+  g_launches += 1;
+  return MAGNET_OK;
+}
+
+int magnet_camera_rays_f32(const double* raw_intrinsics, int32_t B, int32_t H, int32_t W, float* intM_out,
+                           float* rays_out, void* stream) {
+  if (!raw_intrinsics || !intM_out || !rays_out) return MAGNET_ERR_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || B > 65535) return MAGNET_ERR_SHAPE;
+  cudaError_t e = magnet::launch_camera_rays(raw_intrinsics, B, H, W, intM_out, rays_out, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e);
   g_launches += 1;
   return MAGNET_OK;

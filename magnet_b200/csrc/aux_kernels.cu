@@ -170,6 +170,91 @@ __global__ void convex_upsample_bwd_kernel(const float* __restrict__ gout, const
   for (int i = 0; i < 9; ++i) gmask[moff + (size_t)i * k * k * HW] = w[i] * (t[i] - dot);
 }
 
+// SURVEY §8 f-4 — caller-side camera prep on the device.
+// utils/utils.py:72-98 (data_preprocess): nghbr_pose = ext_nghbr * inv(ext_ref); a view is invalid when either
+// extrinsic or the product contains a NaN (then its pose stays zero).  One thread per (b, v); the 4x4 inverse is
+// Gauss-Jordan with partial pivoting in fp32 (the reference: LAPACK sgetri on the fp32 matrix).
+__global__ void relative_poses_kernel(const float* __restrict__ ext_ref, const float* __restrict__ ext_nghbr, int B,
+                                      int V, float* __restrict__ poses, int32_t* __restrict__ valid) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * V) return;
+  const int b = idx / V, v = idx % V;
+  float a[4][8];
+  bool nan_ref = false, nan_n = false;
+  const float* R = ext_ref + (size_t)b * 16;
+  const float* N = ext_nghbr + ((size_t)v * B + b) * 16;           // list over views of (B,4,4), view-major
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      a[i][j] = R[i * 4 + j];
+      a[i][4 + j] = i == j ? 1.0f : 0.0f;
+      nan_ref |= isnan(R[i * 4 + j]);
+      nan_n |= isnan(N[i * 4 + j]);
+    }
+  for (int c = 0; c < 4; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < 4; ++r)
+      if (fabsf(a[r][c]) > fabsf(a[piv][c])) piv = r;
+    for (int j = 0; j < 8; ++j) { const float t = a[c][j]; a[c][j] = a[piv][j]; a[piv][j] = t; }
+    const float inv = 1.0f / a[c][c];
+    for (int j = 0; j < 8; ++j) a[c][j] *= inv;
+    for (int r = 0; r < 4; ++r)
+      if (r != c) {
+        const float f = a[r][c];
+        for (int j = 0; j < 8; ++j) a[r][j] = __fmaf_rn(-f, a[c][j], a[r][j]);
+      }
+  }
+  float out[16];
+  bool nan_p = false;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      float acc = 0.0f;
+      for (int k = 0; k < 4; ++k) acc = __fmaf_rn(N[i * 4 + k], a[k][4 + j], acc);
+      out[i * 4 + j] = acc;
+      nan_p |= isnan(acc);
+    }
+  const bool ok = !(nan_ref || nan_n || nan_p);
+  valid[idx] = ok ? 1 : 0;
+  for (int e = 0; e < 16; ++e) poses[(size_t)idx * 16 + e] = ok ? out[e] : 0.0f;
+}
+
+// data/dataloader_scannet.py:113-153 (get_ray_array + get_cam_intrinsics): quarter-resolution intrinsics and the
+// per-pixel rays K_raw^-1 (x+0.5, y+0.5, 1) scaled to the raw image — evaluated in fp64 like the numpy original and
+// rounded to fp32 once, so the result is bit-identical to the reference's arrays.
+// raw (B,6) doubles: fx, fy, cx, cy (raw image), raw_W, raw_H.
+__global__ void camera_rays_kernel(const double* __restrict__ raw, int H, int W, float* __restrict__ intM,
+                                   float* __restrict__ rays) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t b = blockIdx.y;
+  const double fx = raw[b * 6 + 0], fy = raw[b * 6 + 1], cx = raw[b * 6 + 2], cy = raw[b * 6 + 3];
+  const double rw = raw[b * 6 + 4], rh = raw[b * 6 + 5];
+  if (n == 0) {
+    float* K = intM + b * 9;
+    for (int e = 0; e < 9; ++e) K[e] = 0.0f;
+    K[0] = (float)(fx * ((double)W / rw));
+    K[4] = (float)(fy * ((double)H / rh));
+    K[2] = (float)(cx * ((double)W / rw));
+    K[5] = (float)(cy * ((double)H / rh));
+    K[8] = 1.0f;
+  }
+  if (n >= H * W) return;
+  const int x = n % W, y = n / W;
+  const size_t HW = (size_t)H * W;
+  rays[(b * 3 + 0) * HW + n] = (float)((((double)x + 0.5) * (rw / (double)W) - cx) / fx);
+  rays[(b * 3 + 1) * HW + n] = (float)((((double)y + 0.5) * (rh / (double)H) - cy) / fy);
+  rays[(b * 3 + 2) * HW + n] = 1.0f;
+}
+
+cudaError_t launch_relative_poses(const float* ext_ref, const float* ext_nghbr, int B, int V, float* poses,
+                                  int32_t* valid, cudaStream_t st) {
+  relative_poses_kernel<<<(B * V + 63) / 64, 64, 0, st>>>(ext_ref, ext_nghbr, B, V, poses, valid);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_camera_rays(const double* raw, int B, int H, int W, float* intM, float* rays, cudaStream_t st) {
+  camera_rays_kernel<<<dim3((H * W + 255) / 256, B), 256, 0, st>>>(raw, H, W, intM, rays);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_upsample_fwd(const float* depth, const float* mask, int B, int CH, int H, int W, int k, float* out,
                                 cudaStream_t st) {
   dim3 grid((W * k + 127) / 128, H * k, B);

@@ -233,3 +233,30 @@ class ConvexUpsample(torch.autograd.Function):
 
 def convex_upsample(depth: torch.Tensor, up_mask: torch.Tensor, k: int) -> torch.Tensor:
     return ConvexUpsample.apply(depth, up_mask, k)
+
+
+def relative_poses(ext_ref: torch.Tensor, ext_nghbr: torch.Tensor):
+    """data_preprocess (utils/utils.py:72-98) on the device: ext_ref (B,4,4), ext_nghbr (V,B,4,4) ->
+    (nghbr_poses (B,V,4,4), is_valid (B,V) int32)."""
+    ext_ref = _need_cuda_f32("ext_ref", ext_ref)
+    ext_nghbr = _need_cuda_f32("ext_nghbr", ext_nghbr)
+    V, B = ext_nghbr.shape[0], ext_nghbr.shape[1]
+    poses = torch.empty(B, V, 4, 4, device=ext_ref.device, dtype=torch.float32)
+    valid = torch.empty(B, V, device=ext_ref.device, dtype=torch.int32)
+    check(lib().magnet_relative_poses_f32(ext_ref.data_ptr(), ext_nghbr.data_ptr(), B, V, poses.data_ptr(),
+                                          valid.data_ptr(), _stream()), "magnet_relative_poses_f32")
+    return poses, valid
+
+
+def camera_rays(raw_intrinsics: torch.Tensor, H: int, W: int):
+    """get_cam_intrinsics (data/dataloader_scannet.py:113-153) on the device: raw_intrinsics (B,6) float64
+    [fx, fy, cx, cy, raw_W, raw_H] -> cam_intrins dict {'intM' (B,3,3), 'unit_ray_array_2D' (B,3,H*W)} (device)."""
+    if not raw_intrinsics.is_cuda or raw_intrinsics.dtype != torch.float64:
+        raise _lib.MagnetError("raw_intrinsics must be a CUDA float64 tensor (B,6)")
+    raw_intrinsics = raw_intrinsics.contiguous()
+    B = raw_intrinsics.shape[0]
+    intM = torch.empty(B, 3, 3, device=raw_intrinsics.device, dtype=torch.float32)
+    rays = torch.empty(B, 3, H * W, device=raw_intrinsics.device, dtype=torch.float32)
+    check(lib().magnet_camera_rays_f32(raw_intrinsics.data_ptr(), B, H, W, intM.data_ptr(), rays.data_ptr(), _stream()),
+          "magnet_camera_rays_f32")
+    return {"intM": intM, "unit_ray_array_2D": rays}

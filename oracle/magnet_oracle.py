@@ -35,6 +35,7 @@ from __future__ import annotations
 import numpy as np
 
 __all__ = [
+    "relative_poses", "camera_rays",
     "depth_sampler", "camera_terms", "bilinear_zeros", "cost_volume_cw", "cost_volume_f",
     "gaussian_update", "gaussian_update_backward", "convex_upsample", "softmax",
 ]
@@ -258,3 +259,52 @@ def convex_upsample(depth, up_mask, k, dtype=np.float32):
     up = (m * nb.reshape(N, C, 9, 1, 1, H, W)).sum(axis=2, dtype=dtype)   # (N,C,k,k,H,W)
     up = up.transpose(0, 1, 4, 2, 5, 3)                                    # (N,C,H,k,W,k)
     return up.reshape(N, C, k * H, k * W).astype(dtype)
+
+
+def relative_poses(ext_ref, ext_nghbr):
+    """data_preprocess (utils/utils.py:72-98): ext_ref (B,4,4), ext_nghbr (V,B,4,4) fp32 ->
+    nghbr_poses (B,V,4,4) = ext_nghbr . inv(ext_ref) and is_valid (B,V); NaN in either extrinsic or in the
+    product invalidates the view (its pose stays zero)."""
+    ext_ref = np.asarray(ext_ref, dtype=np.float32)
+    ext_nghbr = np.asarray(ext_nghbr, dtype=np.float32)
+    V, B = ext_nghbr.shape[:2]
+    poses = np.zeros((B, V, 4, 4), dtype=np.float32)
+    valid = np.ones((B, V), dtype=np.int32)
+    for b in range(B):
+        if np.isnan(ext_ref[b]).any():
+            valid[b, :] = 0
+            continue
+        inv = np.linalg.inv(ext_ref[b])
+        for v in range(V):
+            if np.isnan(ext_nghbr[v, b]).any():
+                valid[b, v] = 0
+                continue
+            pose = (ext_nghbr[v, b] @ inv).astype(np.float32)
+            if np.isnan(pose).any():
+                valid[b, v] = 0
+            else:
+                poses[b, v] = pose
+    return poses, valid
+
+
+def camera_rays(raw, H, W):
+    """get_ray_array + get_cam_intrinsics (data/dataloader_scannet.py:113-153): raw (B,6) float64 = fx, fy, cx, cy
+    of the raw image, raw_W, raw_H -> intM (B,3,3) fp32 scaled to the H x W grid, rays (B,3,H*W) fp32 through the
+    pixel centres (x+0.5, y+0.5); everything in fp64 until the final cast, as in the numpy original."""
+    raw = np.asarray(raw, dtype=np.float64)
+    B = raw.shape[0]
+    intM = np.zeros((B, 3, 3), dtype=np.float64)
+    rays = np.ones((B, H, W, 3), dtype=np.float64)
+    xs = np.arange(W, dtype=np.float64) + 0.5
+    ys = np.arange(H, dtype=np.float64) + 0.5
+    for b in range(B):
+        fx, fy, cx, cy, rw, rh = raw[b]
+        intM[b, 2, 2] = 1.0
+        intM[b, 0, 0] = fx * (W / rw)
+        intM[b, 1, 1] = fy * (H / rh)
+        intM[b, 0, 2] = cx * (W / rw)
+        intM[b, 1, 2] = cy * (H / rh)
+        rays[b, :, :, 0] = ((xs * (rw / W)) - cx)[None, :] / fx
+        rays[b, :, :, 1] = ((ys * (rh / H)) - cy)[:, None] / fy
+    rays2d = np.reshape(np.transpose(rays, (0, 3, 1, 2)), (B, 3, H * W))
+    return intM.astype(np.float32), rays2d.astype(np.float32)

@@ -421,3 +421,19 @@ def test_magnet_module_matches_reference_dataflow(cuda):
         d = (a - b).abs()
         assert float(d.median()) <= 1e-5 * float(b.abs().max())
         assert float((d > 1e-3 * float(b.abs().max())).float().mean()) < 2e-3     # downstream of rare mask flips
+
+
+def test_camera_prep_kernels(cuda):
+    """f-4: on-device relative poses + validity against the numpy restatement of data_preprocess, rays / intrinsics
+    bit-identical to the fp64 numpy restatement of get_cam_intrinsics."""
+    from tests.test_oracle_golden import _camera_prep_case
+    ext_ref, ext_nghbr = _camera_prep_case()
+    want_p, want_v = mo.relative_poses(ext_ref, ext_nghbr)
+    poses, valid = ops.relative_poses(torch.from_numpy(ext_ref).to(cuda), torch.from_numpy(ext_nghbr).to(cuda))
+    assert np.array_equal(valid.cpu().numpy(), want_v)
+    assert np.allclose(poses.cpu().numpy(), want_p, rtol=1e-5, atol=2e-6)
+    raw = np.array([[1169.6, 1167.1, 646.3, 489.9, 1296.0, 968.0], [577.9, 578.7, 319.5, 239.5, 640.0, 480.0]])
+    cam = ops.camera_rays(torch.from_numpy(raw).to(cuda), 120, 160)
+    intM, rays = mo.camera_rays(raw, 120, 160)
+    assert np.array_equal(cam["intM"].cpu().numpy(), intM)
+    assert np.array_equal(cam["unit_ray_array_2D"].cpu().numpy(), rays)

@@ -305,6 +305,7 @@ def main():
     # ---- loop including the real G-Net convolutions (PyTorch / cuDNN), reported beside the headline --------
     with_gnet = None
     if not args.no_gnet:
+        torch.backends.cudnn.benchmark = True                      # as the reference's drivers set it (train_MaGNet.py:56)
         torch.manual_seed(0)
         head = magnet_b200.GNET(ch_in=256 + D).to(dev).eval()
         x_d3 = torch.randn(B, 256, H, Wd, device=dev)

@@ -209,7 +209,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--variant", default="auto", choices=["auto", "direct", "cells", "cells_noreuse", "window"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "direct", "cells", "cells_noreuse", "tma"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gnet", action="store_true")
     args = ap.parse_args()
@@ -231,7 +231,7 @@ def main():
     from magnet_b200 import _lib, ops
     from magnet_b200.synthetic import make_config
     variant = {"auto": _lib.VARIANT_AUTO, "direct": _lib.VARIANT_DIRECT, "cells": _lib.VARIANT_CELLS,
-               "cells_noreuse": _lib.VARIANT_CELLS_NOREUSE, "window": _lib.VARIANT_WINDOW}[args.variant]
+               "cells_noreuse": _lib.VARIANT_CELLS_NOREUSE, "tma": _lib.VARIANT_TMA}[args.variant]
 
     inp = make_config(args.config, seed=1 + rank)
     B, V, D = inp.B, inp.V, inp.D

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MAGNET_ABI_VERSION 1
+#define MAGNET_ABI_VERSION 2
 #define MAGNET_MAX_PLANES 256   /* max depth hypotheses / planes per call (D) */
 
 typedef enum magnet_status {
@@ -47,21 +47,26 @@ typedef enum magnet_depth_mode {
 /* Memory layout of the source-view feature maps. */
 typedef enum magnet_src_layout {
   MAGNET_SRC_NCHW = 0,   /* (V*B, C, H, W), the reference layout                               */
-  MAGNET_SRC_TILED32 = 1 /* (V*B, H, ceil(W/32), C/4, 32, 4): per row, tiles of 32 pixels; inside a tile
+  MAGNET_SRC_TILED32 = 1, /* (V*B, H, ceil(W/32), C/4, 32, 4): per row, tiles of 32 pixels; inside a tile
                             the C/4 channel quads are 512 B apart and the 32 pixels of one quad are
                             contiguous (see magnet_repack_tiled32_f32).  Pixels x >= W are padding. */
+  MAGNET_SRC_PIXC = 2     /* (V*B, H, W, C+4): pixel-major, per pixel the C channels followed by the source
+                            Gaussian (mu, sigma) and two zeros (see magnet_repack_pixc_f32): the layout the
+                            TMA-staged production kernel fetches its windows from.  With this layout
+                            magnet_cost_args.src_gmm is ignored (the Gaussians travel inside src_feat). */
 } magnet_src_layout;
 
 /* Kernel selection (for parity cross-checks and profiling). */
 typedef enum magnet_variant {
-  MAGNET_VARIANT_AUTO = 0,   /* production choice                                              */
+  MAGNET_VARIANT_AUTO = 0,   /* production choice: TMA for MAGNET_SRC_PIXC, CELLS for MAGNET_SRC_TILED32,
+                                DIRECT otherwise                                               */
   MAGNET_VARIANT_DIRECT = 1, /* one thread per output, 4 taps x C channels per hypothesis,
                                 reference operation order, fp64 view accumulation             */
   MAGNET_VARIANT_CELLS = 2,  /* tap-sharing kernel: per-lane bilinear-cell records             */
   MAGNET_VARIANT_CELLS_NOREUSE = 3, /* diagnostic: as CELLS, but every cell gathers all 4 taps
                                        (MAGNET_DEPTH_GAUSS only)                               */
-  MAGNET_VARIANT_WINDOW = 4  /* tap-sharing kernel with the CTA's source window staged in shared
-                                memory (cp.async), accumulators in registers                   */
+  MAGNET_VARIANT_TMA = 4     /* production: tap-sharing kernel, 4 lanes per pixel, the CTA's source window
+                                staged in shared memory by TMA (MAGNET_SRC_PIXC only)          */
 } magnet_variant;
 
 /* Per (batch element, view) camera constants, 16 floats, produced by magnet_pack_cameras_f32.
@@ -140,6 +145,12 @@ int magnet_pack_cameras_f32(const float* intM, const float* R, int64_t r_sb, int
                             int64_t r_sj, const float* t, int64_t t_sb, int64_t t_sv, int64_t t_si,
                             const int32_t* is_valid, int32_t B, int32_t V, magnet_camera* cams_out,
                             void* stream);
+
+/* Source repack (N, C, H, W) features [+ (N, 2, H, W) Gaussians, may be NULL -> zeros] -> MAGNET_SRC_PIXC
+ * (N, H, W, C+4); C in {16, 32, 64}, dst 16-byte aligned.  Once per forward (the features do not change across the
+ * N_iter iterations, MAGNET.py:150-169). */
+int magnet_repack_pixc_f32(const float* src_nchw, const float* src_gmm, float* dst, int32_t N, int32_t C, int32_t H,
+                           int32_t W, void* stream);
 
 /* Source-feature repack (N, C, H, W) -> MAGNET_SRC_TILED32 (N, H, ceil(W/32), C/4, 32, 4);
  * C % 4 == 0, dst 16-byte aligned, padding pixels are written as zeros. */

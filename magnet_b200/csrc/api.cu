@@ -12,9 +12,11 @@ cudaError_t launch_cost_direct(const CostParams& p, int depth_mode, int src_layo
 cudaError_t launch_cost_cells(const CostParams& p, int mode, int C, bool cw, bool reuse, cudaStream_t st);
 cudaError_t launch_softmax_planes(float* vol, int B, int D, int HW, cudaStream_t st);
 bool cells_supports(int C, int D, int layout);
-cudaError_t launch_cost_window(const CostParams& p, int mode, int C, bool cw, cudaStream_t st);
-bool window_supports(int C, int D, int layout);
-void window_launch_info(int B, int H, int W, int D, int C, int* grid, int* block, int* smem);
+cudaError_t launch_cost_tma(const CostParams& p, int mode, int C, bool cw, cudaStream_t st);
+bool tma_supports(int C, int D, int V, int layout);
+void tma_launch_info(int B, int H, int W, int D, int* grid, int* block, int* smem);
+cudaError_t launch_repack_pixc(const float* src, const float* gmm, float* dst, int N, int C, int H, int W,
+                               cudaStream_t st);
 void cells_launch_info(int B, int H, int W, int D, int* grid, int* block, int* smem);
 cudaError_t launch_pack_cameras(const float* intM, const float* R, int64_t r_sb, int64_t r_sv, int64_t r_si,
                                 int64_t r_sj, const float* t, int64_t t_sb, int64_t t_sv, int64_t t_si,
@@ -50,7 +52,7 @@ int validate_cost(const magnet_cost_args* a) {
   if (a->D > MAGNET_MAX_PLANES) return MAGNET_ERR_UNSUPPORTED;
   if ((int64_t)a->H * a->W > (1 << 26)) return MAGNET_ERR_SHAPE;
   if (!a->ref_feat || !a->src_feat || !a->rays || !a->cams || !a->out) return MAGNET_ERR_NULL;
-  if (a->consistency && !a->src_gmm) return MAGNET_ERR_NULL;
+  if (a->consistency && !a->src_gmm && a->src_layout != MAGNET_SRC_PIXC) return MAGNET_ERR_NULL;
   if (a->consistency && a->softmax) return MAGNET_ERR_UNSUPPORTED;
   switch (a->depth_mode) {
     case MAGNET_DEPTH_VOLUME: if (!a->d_volume) return MAGNET_ERR_NULL; break;
@@ -61,11 +63,15 @@ int validate_cost(const magnet_cost_args* a) {
   if (a->src_layout == MAGNET_SRC_TILED32) {
     if (a->C % 4 != 0) return MAGNET_ERR_UNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(a->src_feat) % 16 != 0) return MAGNET_ERR_ALIGN;
+  } else if (a->src_layout == MAGNET_SRC_PIXC) {
+    if (!magnet::tma_supports(a->C, a->D, a->V, a->src_layout)) return MAGNET_ERR_UNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(a->src_feat) % 16 != 0) return MAGNET_ERR_ALIGN;
+    if (a->variant != MAGNET_VARIANT_AUTO && a->variant != MAGNET_VARIANT_TMA) return MAGNET_ERR_UNSUPPORTED;
   } else if (a->src_layout != MAGNET_SRC_NCHW) {
     return MAGNET_ERR_UNSUPPORTED;
   }
-  if (a->variant < MAGNET_VARIANT_AUTO || a->variant > MAGNET_VARIANT_WINDOW) return MAGNET_ERR_UNSUPPORTED;
-  if (a->variant == MAGNET_VARIANT_WINDOW && !magnet::window_supports(a->C, a->D, a->src_layout))
+  if (a->variant < MAGNET_VARIANT_AUTO || a->variant > MAGNET_VARIANT_TMA) return MAGNET_ERR_UNSUPPORTED;
+  if (a->variant == MAGNET_VARIANT_TMA && !magnet::tma_supports(a->C, a->D, a->V, a->src_layout))
     return MAGNET_ERR_UNSUPPORTED;
   if ((a->variant == MAGNET_VARIANT_CELLS || a->variant == MAGNET_VARIANT_CELLS_NOREUSE) &&
       !magnet::cells_supports(a->C, a->D, a->src_layout))
@@ -75,13 +81,12 @@ int validate_cost(const magnet_cost_args* a) {
 }
 
 bool use_cells(const magnet_cost_args* a) {
-  if (a->variant == MAGNET_VARIANT_DIRECT || a->variant == MAGNET_VARIANT_WINDOW) return false;
+  if (a->variant == MAGNET_VARIANT_DIRECT || a->variant == MAGNET_VARIANT_TMA) return false;
   return magnet::cells_supports(a->C, a->D, a->src_layout);
 }
 
-bool use_window(const magnet_cost_args* a) {
-  if (a->variant != MAGNET_VARIANT_WINDOW) return false;   // AUTO = global-gather cells kernel (faster today)
-  return magnet::window_supports(a->C, a->D, a->src_layout);
+bool use_tma(const magnet_cost_args* a) {                  // the PIXC layout is served by the TMA kernel only
+  return a->src_layout == MAGNET_SRC_PIXC && magnet::tma_supports(a->C, a->D, a->V, a->src_layout);
 }
 }  // namespace
 
@@ -109,8 +114,8 @@ int magnet_cost_launch_info(const magnet_cost_args* a, int* grid_ctas, int* bloc
   const int st = validate_cost(a);
   if (st != MAGNET_OK) return st;
   if (!grid_ctas || !block_threads || !smem_bytes) return MAGNET_ERR_NULL;
-  if (use_window(a)) {
-    magnet::window_launch_info(a->B, a->H, a->W, a->D, a->C, grid_ctas, block_threads, smem_bytes);
+  if (use_tma(a)) {
+    magnet::tma_launch_info(a->B, a->H, a->W, a->D, grid_ctas, block_threads, smem_bytes);
   } else if (use_cells(a)) {
     magnet::cells_launch_info(a->B, a->H, a->W, a->D, grid_ctas, block_threads, smem_bytes);
   } else {
@@ -136,12 +141,11 @@ int magnet_cost_volume_f32(const magnet_cost_args* a, void* stream) {
   p.k_sorted = 1;
   for (int j = 1; j < a->D; ++j)
     if (!(p.k[j] >= p.k[j - 1])) p.k_sorted = 0;
-  if (getenv("MAGNET_NO_WALK")) p.k_sorted = 0;     // diagnostic: force the exact per-hypothesis cell walk
   int launches = 0;
   cudaError_t e;
-  if (use_window(a) || use_cells(a)) {
-    if (use_window(a))
-      e = magnet::launch_cost_window(p, a->depth_mode, a->C, a->consistency != 0, (cudaStream_t)stream);
+  if (use_tma(a) || use_cells(a)) {
+    if (use_tma(a))
+      e = magnet::launch_cost_tma(p, a->depth_mode, a->C, a->consistency != 0, (cudaStream_t)stream);
     else
       e = magnet::launch_cost_cells(p, a->depth_mode, a->C, a->consistency != 0,
                                     a->variant != MAGNET_VARIANT_CELLS_NOREUSE, (cudaStream_t)stream);
@@ -204,6 +208,18 @@ int magnet_repack_tiled32_f32(const float* src_nchw, float* dst, int32_t N, int3
   if (C % 4 != 0 || C / 4 > 65535 || N > 65535) return MAGNET_ERR_UNSUPPORTED;
   if (reinterpret_cast<uintptr_t>(dst) % 16 != 0) return MAGNET_ERR_ALIGN;
   cudaError_t e = magnet::launch_repack(src_nchw, dst, N, C, H, W, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e);
+  g_launches += 1;
+  return MAGNET_OK;
+}
+
+int magnet_repack_pixc_f32(const float* src_nchw, const float* src_gmm, float* dst, int32_t N, int32_t C, int32_t H,
+                           int32_t W, void* stream) {
+  if (!src_nchw || !dst) return MAGNET_ERR_NULL;
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || N > 65535) return MAGNET_ERR_SHAPE;
+  if (C != 16 && C != 32 && C != 64) return MAGNET_ERR_UNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(dst) % 16 != 0) return MAGNET_ERR_ALIGN;
+  cudaError_t e = magnet::launch_repack_pixc(src_nchw, src_gmm, dst, N, C, H, W, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e);
   g_launches += 1;
   return MAGNET_OK;

@@ -11,8 +11,8 @@ per-(batch, view) Python loop):
     cached across the N_iter calls of one forward (keyed by object identity + version counter);
   * ``R`` / ``t`` arrive as non-contiguous views of ``nghbr_poses`` (MAGNET.py:147-148): passed to
     ``magnet_pack_cameras_f32`` with their strides, no copy;
-  * ``nghbr_feat`` arrives NCHW: repacked once per forward into the (N, C/4, H, W, 4) layout the
-    tap-sharing kernel gathers from (cached the same way).
+  * ``nghbr_feat`` / ``nghbr_gmms`` arrive NCHW: repacked once per forward into the pixel-major PIXC layout the
+    TMA-staged kernel fetches its windows from (cached the same way; bypassed under CUDA-graph capture).
 The CW volume is not differentiable (its inputs never require grad in the reference, SURVEY §3.2);
 the F volume is differentiable w.r.t. both feature maps (magnet_cost_volume_f_bwd_f32) for F-Net training.
 """
@@ -27,21 +27,35 @@ from . import _lib, ops
 
 
 class _PrepCache:
-    """Identity + version keyed cache of per-forward preparations (uploads, repacks, camera tables).
+    """Cache of per-forward preparations (uploads, repacks, camera tables), keyed on the CALLER's tensors.
 
-    An entry is valid only while the *same tensor object* is alive and unmodified: the key holds a
-    weakref to every source tensor and its ``_version``; a freed-and-reallocated tensor at the same
-    address can therefore never alias a stale entry."""
+    An entry is valid only while the same tensor objects are alive and unmodified: the key holds each source
+    tensor's storage pointer, ``_version``, shape, strides and device, plus a weakref to the object the caller
+    passed (never to a ``detach()`` temporary), so a freed-and-reallocated tensor at the same address cannot alias a
+    stale entry.  Writers that do not bump ``_version`` (a CUDA-graph replay, NCCL, a non-torch kernel) are invisible
+    to this key; therefore the cache is BYPASSED while the current stream is being captured (the preparation kernels
+    then become part of the graph and replay with the data), and ``clear_cache()`` / ``prep_cache(False)`` exist for
+    callers that refill buffers behind torch's back."""
 
     def __init__(self, capacity: int = 8):
         self.capacity = capacity
+        self.enabled = True
         self._items: Dict[Tuple, Tuple[tuple, object]] = {}
 
     @staticmethod
     def _sig(tensors):
-        return tuple((id(t), t._version, tuple(t.shape), str(t.device)) for t in tensors)
+        return tuple((t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), str(t.device)) for t in tensors)
+
+    def _usable(self, tensors) -> bool:
+        if not self.enabled:
+            return False
+        if any(t.is_cuda for t in tensors) and torch.cuda.is_current_stream_capturing():
+            return False
+        return True
 
     def get(self, kind: str, tensors, extra=()):
+        if not self._usable(tensors):
+            return None
         key = (kind,) + self._sig(tensors) + tuple(extra)
         hit = self._items.get(key)
         if hit is not None:
@@ -52,6 +66,8 @@ class _PrepCache:
         return None
 
     def put(self, kind: str, tensors, value, extra=()):
+        if not self._usable(tensors):
+            return value
         key = (kind,) + self._sig(tensors) + tuple(extra)
         for dead in [k for k, (refs, _) in self._items.items() if any(r() is None for r in refs)]:
             del self._items[dead]                      # drop preparations whose source tensor is gone
@@ -71,6 +87,13 @@ def clear_cache() -> None:
     _cache.clear()
 
 
+def prep_cache(enabled: bool) -> None:
+    """Enable / disable the per-forward preparation cache (disabled: every call repacks and re-uploads)."""
+    _cache.enabled = bool(enabled)
+    if not enabled:
+        _cache.clear()
+
+
 def _device_intrinsics(cam_intrins, device):
     intM, rays = cam_intrins['intM'], cam_intrins['unit_ray_array_2D']
     hit = _cache.get("intr", (intM, rays), (str(device),))
@@ -82,26 +105,43 @@ def _device_intrinsics(cam_intrins, device):
 
 
 def _camera_table(cam_intrins, R, t, is_valid, device):
+    """K*R, K*t per (b, v): 2 KB, one 3 us kernel.  Cached on the tensors R and t are views OF (MAGNET.py:147-148
+    slices nghbr_poses once per forward) — both bases, with their version counters — plus the views' geometry."""
     intM_d, _ = _device_intrinsics(cam_intrins, device)
-    # R and t are fresh views on every call (MAGNET.py:147-148 slices once per forward, but a caller
-    # may re-slice); key on the storage they view + their layout instead of the view object.
-    base = R._base if R._base is not None else R
-    hit = _cache.get("cams", (base, is_valid, cam_intrins['intM']),
-                     (R.data_ptr(), R.stride(), t.data_ptr(), t.stride()))
+    rbase = R._base if R._base is not None else R
+    tbase = t._base if t._base is not None else t
+    src = (rbase, tbase, is_valid, cam_intrins['intM'])
+    extra = (R.data_ptr(), tuple(R.shape), tuple(R.stride()), t.data_ptr(), tuple(t.shape), tuple(t.stride()))
+    hit = _cache.get("cams", src, extra)
     if hit is not None:
         return hit
     valid_d = is_valid.to(device=device, dtype=torch.int32)
-    cams = ops.pack_cameras(intM_d, R, t, valid_d)
-    return _cache.put("cams", (base, is_valid, cam_intrins['intM']), cams,
-                      (R.data_ptr(), R.stride(), t.data_ptr(), t.stride()))
+    return _cache.put("cams", src, ops.pack_cameras(intM_d, R, t, valid_d), extra)
 
 
-def _packed_source(nghbr_feat):
-    if nghbr_feat.shape[1] % 4 != 0:
-        return nghbr_feat.contiguous(), _lib.SRC_NCHW
+def _wants_pixc(C: int, V: int, variant: int) -> bool:
+    return variant in (_lib.VARIANT_AUTO, _lib.VARIANT_TMA) and C in (16, 32, 64) and V <= 16
+
+
+def _packed_source(nghbr_feat, nghbr_gmms, V, variant):
+    """The source maps in the layout the selected kernel reads, repacked once per forward (cached on the caller's
+    tensor objects): PIXC (features + Gaussians, pixel-major) for the TMA production kernel, TILED32 for the
+    global-gather cross-check kernels, NCHW when the channel count fits neither."""
+    C = nghbr_feat.shape[1]
+    if _wants_pixc(C, V, variant):
+        src = (nghbr_feat,) if nghbr_gmms is None else (nghbr_feat, nghbr_gmms)
+        hit = _cache.get("pixc", src)
+        if hit is None:
+            hit = _cache.put("pixc", src, ops.repack_pixc(nghbr_feat.detach(),
+                                                          None if nghbr_gmms is None else nghbr_gmms.detach()))
+        return hit, _lib.SRC_PIXC
+    if variant == _lib.VARIANT_TMA:
+        raise _lib.MagnetError(f"MAGNET_VARIANT_TMA needs C in (16, 32, 64) and V <= 16, got C={C}, V={V}")
+    if C % 4 != 0:
+        return nghbr_feat.detach().contiguous(), _lib.SRC_NCHW
     hit = _cache.get("tiled32", (nghbr_feat,))
     if hit is None:
-        hit = _cache.put("tiled32", (nghbr_feat,), ops.repack_tiled32(nghbr_feat))
+        hit = _cache.put("tiled32", (nghbr_feat,), ops.repack_tiled32(nghbr_feat.detach()))
     return hit, _lib.SRC_TILED32
 
 
@@ -120,10 +160,19 @@ def est_costvolume_CW(d_volume, ref_feat, nghbr_feat, ref_gmms, nghbr_gmms,
     with torch.no_grad():
         _, rays_d = _device_intrinsics(cam_intrins, device)
         cams = _camera_table(cam_intrins, R, t, is_valid, device)
-        src, layout = _packed_source(nghbr_feat.detach())
+        src, layout = _packed_source(nghbr_feat, nghbr_gmms, V, variant)
         return ops.cost_volume(ref_feat.detach(), src, rays_d, cams, V=V, src_layout=layout, consistency=True,
                                src_gmm=nghbr_gmms.detach(), kappa=float(thres), d_volume=d_volume.detach(),
                                variant=variant)
+
+
+def _plane_list(d_center):
+    """The D plane depths as host floats.  ``d_center`` is a constant of the training run (train_FNet.py:56-66): the
+    device -> host read happens once per tensor, not once per step."""
+    hit = _cache.get("planes", (d_center,))
+    if hit is None:
+        hit = _cache.put("planes", (d_center,), d_center.detach().reshape(-1).cpu().tolist())
+    return hit
 
 
 class _CostVolumeF(torch.autograd.Function):
@@ -131,7 +180,7 @@ class _CostVolumeF(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, ref_feat, nghbr_feat, planes, rays_d, cams, V, variant):
-        src, layout = _packed_source(nghbr_feat.detach())
+        src, layout = _packed_source(nghbr_feat, None, V, variant)
         out = ops.cost_volume(ref_feat.detach(), src, rays_d, cams, V=V, src_layout=layout, consistency=False,
                               k=planes, planes=True, softmax=True, variant=variant)
         ctx.save_for_backward(ref_feat.detach(), nghbr_feat.detach(), out, rays_d, cams)
@@ -152,7 +201,7 @@ def est_costvolume_F(d_center, ref_feat, nghbr_feat, R, t, is_valid, cam_intrins
     device = ref_feat.device
     B = ref_feat.shape[0]
     V = int(nghbr_feat.shape[0] / B)
-    planes = d_center.detach().reshape(-1).cpu().tolist()
+    planes = _plane_list(d_center)
     _, rays_d = _device_intrinsics(cam_intrins, device)
     cams = _camera_table(cam_intrins, R, t, is_valid, device)
     return _CostVolumeF.apply(ref_feat, nghbr_feat, planes, rays_d, cams, V, variant)

@@ -58,7 +58,7 @@ class MatchingPlan:
     device intrinsics / rays, camera-constant table, source features in the gather layout."""
 
     def __init__(self, ref_feat, nghbr_feat, nghbr_gmms, nghbr_poses, is_valid, cam_intrins, *,
-                 thres: int = 5, src_layout: int = _lib.SRC_TILED32):
+                 thres: int = 5, src_layout: int = _lib.SRC_PIXC):
         dev = ref_feat.device
         self.B, self.C, self.H, self.W = ref_feat.shape
         self.V = nghbr_feat.shape[0] // self.B
@@ -69,14 +69,32 @@ class MatchingPlan:
         intM = cam_intrins['intM'].to(dev, torch.float32).contiguous()
         R, t = nghbr_poses[:, :, :3, :3], nghbr_poses[:, :, :3, 3]
         self.cams = ops.pack_cameras(intM, R, t, is_valid.to(dev, torch.int32))
-        if src_layout == _lib.SRC_TILED32 and self.C % 4 == 0:
-            self.src, self.layout = ops.repack_tiled32(nghbr_feat.detach()), _lib.SRC_TILED32
-        else:
-            self.src, self.layout = nghbr_feat.detach().contiguous(), _lib.SRC_NCHW
+        self._nghbr_feat = nghbr_feat.detach()
+        self._packed = {}
+        if src_layout == _lib.SRC_PIXC and not (self.C in (16, 32, 64) and self.V <= 16):
+            src_layout = _lib.SRC_TILED32
+        if src_layout == _lib.SRC_TILED32 and self.C % 4 != 0:
+            src_layout = _lib.SRC_NCHW
+        self.layout = src_layout
+        self.src = self._source(src_layout)
+
+    def _source(self, layout: int):
+        """Source maps in ``layout`` (built on first use; the cross-check variants read other layouts than production)."""
+        if layout not in self._packed:
+            if layout == _lib.SRC_PIXC:
+                self._packed[layout] = ops.repack_pixc(self._nghbr_feat, self.src_gmm)
+            elif layout == _lib.SRC_TILED32:
+                self._packed[layout] = ops.repack_tiled32(self._nghbr_feat)
+            else:
+                self._packed[layout] = self._nghbr_feat.contiguous()
+        return self._packed[layout]
 
     def cost(self, gmm: torch.Tensor, k, out: Optional[torch.Tensor] = None, variant=_lib.VARIANT_AUTO):
         """Fused sampler + CW cost volume for the current Gaussian (B,2,H,W)."""
-        return ops.cost_volume(self.ref_feat, self.src, self.rays, self.cams, V=self.V, src_layout=self.layout,
+        layout = self.layout
+        if variant in (_lib.VARIANT_DIRECT, _lib.VARIANT_CELLS, _lib.VARIANT_CELLS_NOREUSE) and layout == _lib.SRC_PIXC:
+            layout = _lib.SRC_TILED32                      # the cross-check kernels gather from TILED32
+        return ops.cost_volume(self.ref_feat, self._source(layout), self.rays, self.cams, V=self.V, src_layout=layout,
                                consistency=True, src_gmm=self.src_gmm, kappa=self.kappa, ref_gmm=gmm.detach(),
                                k=k, out=out, variant=variant)
 

@@ -71,6 +71,25 @@ def repack_tiled32(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch
     return out
 
 
+def repack_pixc(x: torch.Tensor, gmm: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(N,C,H,W) features [+ (N,2,H,W) Gaussians] -> PIXC (N, H, W, C+4): pixel-major, per pixel the C channels then
+    (mu, sigma, 0, 0) — the layout the TMA-staged production kernel fetches its windows from.  C in {16, 32, 64}."""
+    x = _need_cuda_f32("x", x)
+    N, Cc, H, W = x.shape
+    gptr = None
+    if gmm is not None:
+        gmm = _need_cuda_f32("gmm", gmm)
+        if tuple(gmm.shape) != (N, 2, H, W):
+            raise _lib.MagnetError(f"gmm must be (N,2,H,W) = {(N, 2, H, W)}, got {tuple(gmm.shape)}")
+        gptr = gmm.data_ptr()
+    if out is None:
+        out = torch.empty(N, H, W, Cc + 4, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(lib().magnet_repack_pixc_f32(x.data_ptr(), gptr, out.data_ptr(), N, Cc, H, W, _stream()),
+              "magnet_repack_pixc_f32")
+    return out
+
+
 def sample_depths(gmm: torch.Tensor, k, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Sampler alone (MAGNET.py:154-156): gmm (B,2,H,W) -> d_volume (B,D,H,W)."""
     gmm = _need_cuda_f32("gmm", gmm)
@@ -105,7 +124,7 @@ def cost_volume(ref_feat: torch.Tensor, src_feat: torch.Tensor, rays: torch.Tens
     a.kappa = float(kappa)
     a.ref_feat, a.src_feat, a.rays, a.cams = ref_feat.data_ptr(), src_feat.data_ptr(), rays.data_ptr(), cams.data_ptr()
     keep = [ref_feat, src_feat, rays, cams]
-    if consistency:
+    if consistency and src_layout != _lib.SRC_PIXC:          # PIXC carries the source Gaussians inside src_feat
         src_gmm = _need_cuda_f32("src_gmm", src_gmm)
         a.src_gmm = src_gmm.data_ptr()
         keep.append(src_gmm)
@@ -162,7 +181,8 @@ def cost_launch_info(B, V, D, Cc, H, W, variant=_lib.VARIANT_AUTO):
     """(grid CTAs, threads per CTA, dynamic smem bytes) the cost kernel would use for these sizes."""
     a = CostArgs()
     a.B, a.V, a.D, a.C, a.H, a.W = B, V, D, Cc, H, W
-    a.depth_mode, a.src_layout, a.consistency, a.variant = _lib.DEPTH_PLANES, _lib.SRC_TILED32, 0, variant
+    layout = _lib.SRC_PIXC if variant in (_lib.VARIANT_AUTO, _lib.VARIANT_TMA) else _lib.SRC_TILED32
+    a.depth_mode, a.src_layout, a.consistency, a.variant = _lib.DEPTH_PLANES, layout, 0, variant
     one = C.c_void_p(0x1000)                       # never dereferenced: validated for non-NULL / alignment only
     a.ref_feat = a.src_feat = a.rays = a.cams = a.out = a.k_host = one
     g, b, s = C.c_int(), C.c_int(), C.c_int()

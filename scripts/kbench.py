@@ -7,7 +7,7 @@ import magnet_b200
 from magnet_b200 import _lib, ops
 from magnet_b200.synthetic import make_config
 cfg = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
-variant = {"auto": 0, "direct": 1, "cells": 2, "noreuse": 3, "window": 4}[(sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] else "auto")]
+variant = {"auto": 0, "direct": 1, "cells": 2, "noreuse": 3, "tma": 4}[(sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] else "auto")]
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 30
 inp = make_config(cfg, seed=1)
 g = inp.to("cuda")

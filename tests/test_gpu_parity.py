@@ -16,7 +16,7 @@ from tests.util import compare_volume, golden_inputs, load_golden, oracle_cw
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [("direct", _lib.VARIANT_DIRECT), ("cells", _lib.VARIANT_CELLS), ("window", _lib.VARIANT_WINDOW)]
+VARIANTS = [("direct", _lib.VARIANT_DIRECT), ("cells", _lib.VARIANT_CELLS), ("tma", _lib.VARIANT_TMA)]
 
 
 def _run_cw(inp, dvol, dev, variant):
@@ -98,7 +98,8 @@ def test_fused_sampler_equals_drop_in(cuda):
     dr = (rev.flip(1) - fused).abs()
     assert float((dr > 1e-5 * scale).float().mean()) <= 2e-5 and float(dr.median()) <= 1e-6 * scale
     noreuse = plan.cost(g.ref_gmms, inp.k.tolist(), variant=_lib.VARIANT_CELLS_NOREUSE)
-    assert torch.equal(fused, noreuse), "register tap reuse must not change a single bit"
+    assert torch.equal(plan.cost(g.ref_gmms, inp.k.tolist(), variant=_lib.VARIANT_CELLS), noreuse), \
+        "register tap reuse must not change a single bit"
     d_nchw = ops.cost_volume(g.ref_feat, g.nghbr_feat, plan.rays, plan.cams, V=inp.V, src_layout=_lib.SRC_NCHW,
                              consistency=True, src_gmm=g.nghbr_gmms, kappa=5.0, ref_gmm=g.ref_gmms, k=inp.k.tolist(),
                              variant=_lib.VARIANT_DIRECT)
@@ -185,11 +186,12 @@ def test_full_size_properties_cfg2(cuda):
     plan = magnet_b200.MatchingPlan(g.ref_feat, g.nghbr_feat, g.nghbr_gmms, g.nghbr_poses, inp.is_valid,
                                     inp.cam_intrins, thres=5)
     k = inp.k.tolist()
-    cells = plan.cost(g.ref_gmms, k, variant=_lib.VARIANT_WINDOW)
+    cells = plan.cost(g.ref_gmms, k, variant=_lib.VARIANT_TMA)
     direct = plan.cost(g.ref_gmms, k, variant=_lib.VARIANT_DIRECT)
-    assert torch.equal(plan.cost(g.ref_gmms, k, variant=_lib.VARIANT_CELLS), cells), \
-        "global-gather and window-staged kernels run the same arithmetic"
+    gather = plan.cost(g.ref_gmms, k, variant=_lib.VARIANT_CELLS)
     assert torch.isfinite(cells).all()
+    dg = (gather - direct).abs()
+    assert float((dg > 1e-4 * float(direct.abs().max())).float().mean()) <= 3e-5
     assert float(cells[3].abs().max()) == 0.0
     scale = float(direct.abs().max())
     d = (cells - direct).abs()
@@ -199,14 +201,14 @@ def test_full_size_properties_cfg2(cuda):
     assert frac_bad <= 3e-5
     plan2 = magnet_b200.MatchingPlan(g.ref_feat * 2.0, g.nghbr_feat, g.nghbr_gmms, g.nghbr_poses, inp.is_valid,
                                      inp.cam_intrins, thres=5)
-    assert torch.equal(plan2.cost(g.ref_gmms, k, variant=_lib.VARIANT_WINDOW), cells * 2.0)
+    assert torch.equal(plan2.cost(g.ref_gmms, k, variant=_lib.VARIANT_TMA), cells * 2.0)
     # reverse the view order (features, Gaussians, poses, validity all permuted consistently)
     B, V = inp.B, inp.V
     perm = torch.arange(V - 1, -1, -1)
     idx = (perm[:, None] * B + torch.arange(B)[None]).reshape(-1).to(cuda)
     plan3 = magnet_b200.MatchingPlan(g.ref_feat, g.nghbr_feat[idx], g.nghbr_gmms[idx], g.nghbr_poses[:, perm.to(cuda)],
                                      inp.is_valid[:, perm], inp.cam_intrins, thres=5)
-    rev = plan3.cost(g.ref_gmms, k, variant=_lib.VARIANT_WINDOW)
+    rev = plan3.cost(g.ref_gmms, k, variant=_lib.VARIANT_TMA)
     assert float((rev - cells).abs().max()) <= 2e-6 * scale
 
 

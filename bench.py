@@ -2,7 +2,7 @@
 """bench.py — frames/s of MaGNet's multi-view matching hot path on B200 (BASELINE.json metric).
 
 One *step* = one pass of the hot path over one batch of synthetic frames per GPU:
-    source repack (NCHW -> TILED32) + camera table  [once per batch, inside the timed region]
+    source repack (NCHW -> PIXC: pixel-major features + Gaussians) + camera table  [once per batch, timed]
     N_iter = 3 x ( fused sampler + warp + bilinear sample + consistency + view fusion kernel
                    -> Gaussian update kernel on a fixed synthetic G-Net output )
 A *frame* is one reference image's full matching loop (SURVEY §8 d).  Workload at N=1 is BASELINE.json
@@ -136,6 +136,25 @@ class ClockSampler:
                 "how": "pynvml, %.0f ms period, during the timed region(s)" % (self.period * 1e3)}
 
 
+def pin_to_gpu_cpus(index):
+    """Pin this process to the CPU cores NVML reports as local to GPU ``index`` (the NUMA node the GPU hangs off): with
+    8 ranks on a two-socket host the launch threads otherwise wander across sockets.  Returns the core count or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def cpu_reference_frames(frames_cfg, steps, warmup, threads=None, budget_s=None):
     """Time the reference's CPU operator sequence (oracle/torch_ref.py: sampler -> est_costvolume_CW ->
     Gaussian update, N_ITER iterations) on 1-frame batches of the same workload.  Returns (frames/s, info)."""
@@ -245,20 +264,26 @@ def main():
     is_valid_d = inp.is_valid.to(dev)
     intM_d = inp.cam_intrins['intM'].to(dev)
     rays_d = inp.cam_intrins['unit_ray_array_2D'].to(dev).contiguous()
-    src_packed = torch.empty(V * B, H, (Wd + 31) // 32, C // 4, 32, 4, device=dev)
+    pixc = variant in (_lib.VARIANT_AUTO, _lib.VARIANT_TMA)           # production layout; the cross-check kernels read TILED32
+    layout = _lib.SRC_PIXC if pixc else _lib.SRC_TILED32
+    src_packed = (torch.empty(V * B, H, Wd, C + 4, device=dev) if pixc
+                  else torch.empty(V * B, H, (Wd + 31) // 32, C // 4, 32, 4, device=dev))
     cv = torch.empty(B, D, H, Wd, device=dev)
     ev_pairs = []
 
     def hot_step(record=False):
         """repack + camera table + N_ITER x (fused cost kernel -> update kernel); everything device-resident."""
-        ops.repack_tiled32(g.nghbr_feat, out=src_packed)
+        if pixc:
+            ops.repack_pixc(g.nghbr_feat, g.nghbr_gmms, out=src_packed)
+        else:
+            ops.repack_tiled32(g.nghbr_feat, out=src_packed)
         cams = ops.pack_cameras(intM_d, g.R, g.t, is_valid_d)
         pred = g.ref_gmms
         for _ in range(N_ITER):
             if record:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            ops.cost_volume(g.ref_feat, src_packed, rays_d, cams, V=V, src_layout=_lib.SRC_TILED32, consistency=True,
+            ops.cost_volume(g.ref_feat, src_packed, rays_d, cams, V=V, src_layout=layout, consistency=True,
                             src_gmm=g.nghbr_gmms, kappa=float(inp.thres), ref_gmm=pred, k=karr, out=cv, variant=variant)
             if record:
                 e1.record()
@@ -282,23 +307,48 @@ def main():
         md.barrier()
         return md.max_over_ranks(s.elapsed_time(e), device=dev)
 
+    affinity = pin_to_gpu_cpus(local_rank)                           # each rank on the cores next to its GPU
     sampler = ClockSampler(index=local_rank) if rank == 0 else None
     with torch.no_grad():
         for _ in range(W):
             hot_step()
         l0 = _lib.launch_count()
-        ms_total = timed(lambda: hot_step(record=True), K, sampler)
-        launches = _lib.launch_count() - l0
+        hot_step()
+        launches_per_step = _lib.launch_count() - l0
+        torch.cuda.synchronize()
+        # The step is launch-latency sensitive (8 short kernels): capture it once per rank in a CUDA graph (SURVEY §7
+        # step 5) and time K replays — one host call per step, identical kernels and arguments.
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                graph_pred = hot_step()
+        torch.cuda.current_stream().wait_stream(side)
+        eager_pred = hot_step()
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+        graph_ok = bool(torch.equal(graph_pred, eager_pred))
+        ms_total = timed(graph.replay, K, sampler)
+        launches = launches_per_step * K
+        # spread: the same K-step region repeated (median / min / max of the max-over-ranks time per step)
+        reps = sorted(timed(graph.replay, K) / K for _ in range(20))
+        # eager, instrumented: CUDA events around every cost-kernel launch (a graph has no per-kernel events)
+        ms_eager = timed(lambda: hot_step(record=True), min(K, 50)) / min(K, 50)
     ms_step = ms_total / K
     frames_per_s = world * B * 1e3 / ms_step
     kern_ms = sum(a.elapsed_time(b) for a, b in ev_pairs) / max(1, len(ev_pairs))
+    repeats = {"regions": len(reps), "median_ms_per_step": reps[len(reps) // 2], "min_ms_per_step": reps[0],
+               "max_ms_per_step": reps[-1], "eager_ms_per_step": ms_eager, "graph_equals_eager": graph_ok,
+               "cpu_affinity": affinity}
     if sampler and len(sampler.samples) < 5:
         # timed region too short for the sampler: keep the identical load running while sampling
         with torch.no_grad():
             sampler.start()
             t_end = time.time() + 1.0
             while time.time() < t_end:
-                hot_step()
+                graph.replay()
             torch.cuda.synchronize()
             sampler.stop()
 
@@ -391,20 +441,30 @@ def main():
             e.record()
         e2e_run(3)
         torch.cuda.synchronize()
-        ke = max(3, K // 10)
-        md.barrier()
-        torch.cuda.synchronize()
-        t_s, t_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_s.record()
-        e2e_run(ke)
-        torch.cuda.synchronize()                                   # includes the copy stream
-        t_e.record()
-        torch.cuda.synchronize()
-        md.barrier()
-        ms_e = md.max_over_ranks(t_s.elapsed_time(t_e), device=dev) / ke
+        # K steps per timed region (the same K as the device-timed arm); regions are repeated until at least 0.5 s of
+        # e2e work has been timed, the MEDIAN region is reported (max over ranks per region)
+        ke = K
+        regions = []
+        total_ms = 0.0
+        while total_ms < 500.0 and len(regions) < 50:
+            md.barrier()
+            torch.cuda.synchronize()
+            t_s, t_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t_s.record()
+            e2e_run(ke)
+            torch.cuda.synchronize()                               # includes the copy stream
+            t_e.record()
+            torch.cuda.synchronize()
+            md.barrier()
+            ms_r = md.max_over_ranks(t_s.elapsed_time(t_e), device=dev)
+            regions.append(ms_r / ke)
+            total_ms += ms_r
+        regions.sort()
+        ms_e = regions[len(regions) // 2]
     e2e = {"value": world * B * 1e3 / ms_e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": ms_e, "api": "sample_depths + est_costvolume_CW (drop-in, d_volume mode) + gaussian_update",
-           "steps": ke, "pipeline": "double-buffered: H2D of step s+1 on a copy stream overlaps the kernels of step s"}
+           "steps": ke, "regions": len(regions), "min_ms_per_step": regions[0], "max_ms_per_step": regions[-1],
+           "pipeline": "double-buffered: H2D of step s+1 on a copy stream overlaps the kernels of step s"}
 
     if rank != 0:
         md.shutdown()
@@ -414,7 +474,11 @@ def main():
     achieved = abytes / (kern_ms * 1e-3) / 1e9
     grid, block, smem = ops.cost_launch_info(B, V, D, C, H, Wd, variant=_lib.VARIANT_CELLS if variant == _lib.VARIANT_CELLS_NOREUSE else variant)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(args.config), "kernel": "cost_cells_kernel<64,GAUSS,CW> (TILED32 gather)" if variant != _lib.VARIANT_DIRECT else "cost_direct_kernel<CW>",
+                "traffic": ncu_traffic(args.config), "kernel": {_lib.VARIANT_DIRECT: "cost_direct_kernel<CW>", _lib.VARIANT_CELLS: "cost_cells_kernel<64,GAUSS,CW> (TILED32 gather)",
+                           _lib.VARIANT_CELLS_NOREUSE: "cost_cells_kernel<64,GAUSS,CW,noreuse>"}.get(
+                               variant, "cost_tma_kernel<64,GAUSS,CW> (PIXC layout, TMA-staged window)"),
+                "kernel_ms_how": "CUDA events around every cost-kernel launch of %d eager steps run right after the "
+                                 "graph-replayed timed region (same kernels, arguments and buffers)" % min(K, 50),
                 "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src,
                 "launch": {"grid": grid, "block": block, "smem_bytes": smem}}
     # ---- reference-CUDA baseline (north_star / BASELINE.md §2): the reference's operator sequence (repeat,
@@ -471,10 +535,13 @@ def main():
         "config": {"workload": WORKLOADS[args.config], "frames_per_step_per_gpu": B, "n_iter": N_ITER, "views": V,
                    "hypotheses": D, "channels": C, "grid": [H, Wd], "depth": inp.meta["depth"], "variant": args.variant,
                    "cache": "inputs_larger_than_l2 (%.0f MB resident per step vs 126 MB L2)" % ((abytes + 4 * V * B * C * HW) / 1e6),
-                   "step": "repack + camera table + %d x (fused cost kernel + update kernel)" % N_ITER},
+                   "step": "repack + camera table + %d x (fused cost kernel + update kernel), one CUDA graph per rank, "
+                           "K replays timed" % N_ITER},
         "clocks": sampler.report() if sampler else None,
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "reference_cuda": reference_cuda, "with_gnet": with_gnet,
+        "reference_cuda": reference_cuda, "with_gnet": with_gnet, "repeats": repeats,
+        "gpu_launches_how": "%d kernels per step (counted by the library on an eager step) x %d graph replays" % (
+            launches_per_step, K),
     }
     print(json.dumps(line), flush=True)
     md.shutdown()

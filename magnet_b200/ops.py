@@ -14,8 +14,27 @@ from . import _lib
 from ._lib import CostArgs, check, lib
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream(dev=None) -> int:
+    """The current stream of the device the operands live on (not of whatever device happens to be current)."""
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _same_device(*named):
+    """All operands of one launch must live on one CUDA device; returns it."""
+    dev = None
+    for name, x in named:
+        if x is None:
+            continue
+        if dev is None:
+            dev = x.device
+        elif x.device != dev:
+            raise _lib.MagnetError(f"{name} is on {x.device}, expected {dev} (all operands of a launch share one device)")
+    return dev
+
+
+def _expect(name: str, x: torch.Tensor, shape) -> None:
+    if tuple(x.shape) != tuple(shape):
+        raise _lib.MagnetError(f"{name} must have shape {tuple(shape)}, got {tuple(x.shape)}")
 
 
 def _need_cuda_f32(name: str, x: torch.Tensor, contiguous: bool = True) -> torch.Tensor:
@@ -53,9 +72,11 @@ def pack_cameras(intM: torch.Tensor, R: torch.Tensor, t: torch.Tensor, is_valid:
     is_valid = is_valid.contiguous()
     cams = torch.empty(B * V, 16, device=intM.device, dtype=torch.float32)
     rs, ts = R.stride(), t.stride()
-    check(lib().magnet_pack_cameras_f32(intM.data_ptr(), R.data_ptr(), rs[0], rs[1], rs[2], rs[3],
-                                        t.data_ptr(), ts[0], ts[1], ts[2], is_valid.data_ptr(), B, V,
-                                        cams.data_ptr(), _stream()), "magnet_pack_cameras_f32")
+    dev = _same_device(("intM", intM), ("R", R), ("t", t), ("is_valid", is_valid))
+    with torch.cuda.device(dev):
+        check(lib().magnet_pack_cameras_f32(intM.data_ptr(), R.data_ptr(), rs[0], rs[1], rs[2], rs[3],
+                                            t.data_ptr(), ts[0], ts[1], ts[2], is_valid.data_ptr(), B, V,
+                                            cams.data_ptr(), _stream(dev)), "magnet_pack_cameras_f32")
     return cams
 
 
@@ -66,8 +87,9 @@ def repack_tiled32(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch
     N, Cc, H, W = x.shape
     if out is None:
         out = torch.empty(N, H, (W + 31) // 32, Cc // 4, 32, 4, device=x.device, dtype=torch.float32)
-    check(lib().magnet_repack_tiled32_f32(x.data_ptr(), out.data_ptr(), N, Cc, H, W, _stream()),
-          "magnet_repack_tiled32_f32")
+    with torch.cuda.device(x.device):
+        check(lib().magnet_repack_tiled32_f32(x.data_ptr(), out.data_ptr(), N, Cc, H, W, _stream(x.device)),
+              "magnet_repack_tiled32_f32")
     return out
 
 
@@ -85,7 +107,7 @@ def repack_pixc(x: torch.Tensor, gmm: Optional[torch.Tensor] = None, out: Option
     if out is None:
         out = torch.empty(N, H, W, Cc + 4, device=x.device, dtype=torch.float32)
     with torch.cuda.device(x.device):
-        check(lib().magnet_repack_pixc_f32(x.data_ptr(), gptr, out.data_ptr(), N, Cc, H, W, _stream()),
+        check(lib().magnet_repack_pixc_f32(x.data_ptr(), gptr, out.data_ptr(), N, Cc, H, W, _stream(x.device)),
               "magnet_repack_pixc_f32")
     return out
 
@@ -98,8 +120,9 @@ def sample_depths(gmm: torch.Tensor, k, out: Optional[torch.Tensor] = None) -> t
     D = len(karr)
     if out is None:
         out = torch.empty(B, D, H, W, device=gmm.device, dtype=torch.float32)
-    check(lib().magnet_sample_depths_f32(gmm.data_ptr(), C.cast(karr, C.c_void_p), B, D, H * W, out.data_ptr(),
-                                         _stream()), "magnet_sample_depths_f32")
+    with torch.cuda.device(gmm.device):
+        check(lib().magnet_sample_depths_f32(gmm.data_ptr(), C.cast(karr, C.c_void_p), B, D, H * W, out.data_ptr(),
+                                             _stream(gmm.device)), "magnet_sample_depths_f32")
     return out
 
 
@@ -114,7 +137,22 @@ def cost_volume(ref_feat: torch.Tensor, src_feat: torch.Tensor, rays: torch.Tens
     src_feat = _need_cuda_f32("src_feat", src_feat)
     rays = _need_cuda_f32("rays", rays)
     cams = _need_cuda_f32("cams", cams)
+    if ref_feat.dim() != 4:
+        raise _lib.MagnetError(f"ref_feat must be (B,C,H,W), got {tuple(ref_feat.shape)}")
     B, Cc, H, W = ref_feat.shape
+    if V <= 0:
+        raise _lib.MagnetError(f"V must be positive, got {V}")
+    # every operand against (B, V, D, C, H, W): a mismatch would read out of bounds, the reference raises instead
+    src_shape = {_lib.SRC_NCHW: (V * B, Cc, H, W), _lib.SRC_TILED32: (V * B, H, (W + 31) // 32, Cc // 4, 32, 4),
+                 _lib.SRC_PIXC: (V * B, H, W, Cc + 4)}.get(src_layout)
+    if src_shape is None:
+        raise _lib.MagnetError(f"unknown src_layout {src_layout}")
+    _expect("src_feat", src_feat, src_shape)
+    _expect("rays", rays, (B, 3, H * W))
+    if cams.numel() != B * V * 16:
+        raise _lib.MagnetError(f"cams must hold B*V = {B * V} camera records of 16 floats, got {tuple(cams.shape)}")
+    dev = _same_device(("ref_feat", ref_feat), ("src_feat", src_feat), ("rays", rays), ("cams", cams),
+                       ("src_gmm", src_gmm), ("d_volume", d_volume), ("ref_gmm", ref_gmm), ("out", out))
     a = CostArgs()
     a.B, a.V, a.C, a.H, a.W = B, V, Cc, H, W
     a.src_layout = src_layout
@@ -126,11 +164,14 @@ def cost_volume(ref_feat: torch.Tensor, src_feat: torch.Tensor, rays: torch.Tens
     keep = [ref_feat, src_feat, rays, cams]
     if consistency and src_layout != _lib.SRC_PIXC:          # PIXC carries the source Gaussians inside src_feat
         src_gmm = _need_cuda_f32("src_gmm", src_gmm)
+        _expect("src_gmm", src_gmm, (V * B, 2, H, W))
         a.src_gmm = src_gmm.data_ptr()
         keep.append(src_gmm)
     karr = None
     if d_volume is not None:
         d_volume = _need_cuda_f32("d_volume", d_volume)
+        if d_volume.dim() != 4 or d_volume.shape[0] != B or tuple(d_volume.shape[2:]) != (H, W):
+            raise _lib.MagnetError(f"d_volume must be (B,D,H,W) = ({B},D,{H},{W}), got {tuple(d_volume.shape)}")
         a.depth_mode, a.D, a.d_volume = _lib.DEPTH_VOLUME, d_volume.shape[1], d_volume.data_ptr()
         keep.append(d_volume)
     else:
@@ -141,12 +182,17 @@ def cost_volume(ref_feat: torch.Tensor, src_feat: torch.Tensor, rays: torch.Tens
             a.depth_mode = _lib.DEPTH_PLANES
         else:
             ref_gmm = _need_cuda_f32("ref_gmm", ref_gmm)
+            _expect("ref_gmm", ref_gmm, (B, 2, H, W))
             a.depth_mode, a.ref_gmm = _lib.DEPTH_GAUSS, ref_gmm.data_ptr()
             keep.append(ref_gmm)
     if out is None:
         out = torch.empty(B, a.D, H, W, device=ref_feat.device, dtype=torch.float32)
+    else:
+        out = _need_cuda_f32("out", out)
+        _expect("out", out, (B, a.D, H, W))
     a.out = out.data_ptr()
-    check(lib().magnet_cost_volume_f32(C.byref(a), _stream()), "magnet_cost_volume_f32")
+    with torch.cuda.device(dev):
+        check(lib().magnet_cost_volume_f32(C.byref(a), _stream(dev)), "magnet_cost_volume_f32")
     return out
 
 
@@ -161,6 +207,14 @@ def cost_volume_f_bwd(ref_feat, src_feat_nchw, rays, cams, planes, V, prob, grad
     grad_out = _need_cuda_f32("grad_out", grad_out)
     B, Cc, H, W = ref_feat.shape
     karr = planes if isinstance(planes, C.Array) else k_array(planes)
+    _expect("src_feat", src, (V * B, Cc, H, W))
+    _expect("rays", rays, (B, 3, H * W))
+    _expect("prob", prob, (B, len(karr), H, W))
+    _expect("grad_out", grad_out, (B, len(karr), H, W))
+    if cams.numel() != B * V * 16:
+        raise _lib.MagnetError(f"cams must hold B*V = {B * V} camera records of 16 floats, got {tuple(cams.shape)}")
+    dev = _same_device(("ref_feat", ref_feat), ("src_feat", src), ("rays", rays), ("cams", cams), ("prob", prob),
+                       ("grad_out", grad_out))
     a = CostArgs()
     a.B, a.V, a.D, a.C, a.H, a.W = B, V, len(karr), Cc, H, W
     a.depth_mode, a.src_layout, a.consistency, a.softmax = _lib.DEPTH_PLANES, _lib.SRC_NCHW, 0, 1 if softmax else 0
@@ -173,7 +227,8 @@ def cost_volume_f_bwd(ref_feat, src_feat_nchw, rays, cams, planes, V, prob, grad
     bw.fwd = C.pointer(a)
     bw.prob, bw.grad_out, bw.workspace = prob.data_ptr(), grad_out.data_ptr(), work.data_ptr()
     bw.grad_ref, bw.grad_src = g_ref.data_ptr(), g_src.data_ptr()
-    check(lib().magnet_cost_volume_f_bwd_f32(C.byref(bw), _stream()), "magnet_cost_volume_f_bwd_f32")
+    with torch.cuda.device(dev):
+        check(lib().magnet_cost_volume_f_bwd_f32(C.byref(bw), _stream(dev)), "magnet_cost_volume_f_bwd_f32")
     return g_ref, g_src
 
 
@@ -200,8 +255,11 @@ class GaussianUpdate(torch.autograd.Function):
         ref_gmm = _need_cuda_f32("ref_gmm", ref_gmm.detach())
         B, _, H, W = d_output.shape
         out = torch.empty_like(d_output)
-        check(lib().magnet_gaussian_update_fwd_f32(d_output.data_ptr(), ref_gmm.data_ptr(), B, H * W,
-                                                   out.data_ptr(), _stream()), "magnet_gaussian_update_fwd_f32")
+        _expect("ref_gmm", ref_gmm, d_output.shape)
+        dev = _same_device(("d_output", d_output), ("ref_gmm", ref_gmm))
+        with torch.cuda.device(dev):
+            check(lib().magnet_gaussian_update_fwd_f32(d_output.data_ptr(), ref_gmm.data_ptr(), B, H * W,
+                                                       out.data_ptr(), _stream(dev)), "magnet_gaussian_update_fwd_f32")
         ctx.save_for_backward(d_output, ref_gmm)
         return out
 
@@ -211,9 +269,10 @@ class GaussianUpdate(torch.autograd.Function):
         grad_out = _need_cuda_f32("grad_out", grad_out)
         B, _, H, W = d_output.shape
         gin = torch.empty_like(d_output)
-        check(lib().magnet_gaussian_update_bwd_f32(grad_out.data_ptr(), d_output.data_ptr(), ref_gmm.data_ptr(),
-                                                   B, H * W, gin.data_ptr(), _stream()),
-              "magnet_gaussian_update_bwd_f32")
+        with torch.cuda.device(d_output.device):
+            check(lib().magnet_gaussian_update_bwd_f32(grad_out.data_ptr(), d_output.data_ptr(), ref_gmm.data_ptr(),
+                                                       B, H * W, gin.data_ptr(), _stream(d_output.device)),
+                  "magnet_gaussian_update_bwd_f32")
         return gin, None
 
 
@@ -232,8 +291,10 @@ class ConvexUpsample(torch.autograd.Function):
         if up_mask.shape != (B, 9 * k * k, H, W):
             raise _lib.MagnetError(f"up_mask must be (B, 9*k*k, H, W) = {(B, 9 * k * k, H, W)}, got {tuple(up_mask.shape)}")
         out = torch.empty(B, CH, k * H, k * W, device=depth.device, dtype=torch.float32)
-        check(lib().magnet_convex_upsample_fwd_f32(depth.data_ptr(), up_mask.data_ptr(), B, CH, H, W, k, out.data_ptr(),
-                                                   _stream()), "magnet_convex_upsample_fwd_f32")
+        dev = _same_device(("depth", depth), ("up_mask", up_mask))
+        with torch.cuda.device(dev):
+            check(lib().magnet_convex_upsample_fwd_f32(depth.data_ptr(), up_mask.data_ptr(), B, CH, H, W, k,
+                                                       out.data_ptr(), _stream(dev)), "magnet_convex_upsample_fwd_f32")
         ctx.save_for_backward(depth, up_mask)
         ctx.k = k
         return out
@@ -245,9 +306,10 @@ class ConvexUpsample(torch.autograd.Function):
         B, CH, H, W = depth.shape
         g_depth = torch.zeros_like(depth)
         g_mask = torch.empty_like(up_mask)
-        check(lib().magnet_convex_upsample_bwd_f32(grad_out.data_ptr(), depth.data_ptr(), up_mask.data_ptr(), B, CH, H, W,
-                                                   ctx.k, g_depth.data_ptr(), g_mask.data_ptr(), _stream()),
-              "magnet_convex_upsample_bwd_f32")
+        with torch.cuda.device(depth.device):
+            check(lib().magnet_convex_upsample_bwd_f32(grad_out.data_ptr(), depth.data_ptr(), up_mask.data_ptr(), B, CH, H,
+                                                       W, ctx.k, g_depth.data_ptr(), g_mask.data_ptr(),
+                                                       _stream(depth.device)), "magnet_convex_upsample_bwd_f32")
         return g_depth, g_mask, None
 
 
@@ -263,8 +325,10 @@ def relative_poses(ext_ref: torch.Tensor, ext_nghbr: torch.Tensor):
     V, B = ext_nghbr.shape[0], ext_nghbr.shape[1]
     poses = torch.empty(B, V, 4, 4, device=ext_ref.device, dtype=torch.float32)
     valid = torch.empty(B, V, device=ext_ref.device, dtype=torch.int32)
-    check(lib().magnet_relative_poses_f32(ext_ref.data_ptr(), ext_nghbr.data_ptr(), B, V, poses.data_ptr(),
-                                          valid.data_ptr(), _stream()), "magnet_relative_poses_f32")
+    dev = _same_device(("ext_ref", ext_ref), ("ext_nghbr", ext_nghbr))
+    with torch.cuda.device(dev):
+        check(lib().magnet_relative_poses_f32(ext_ref.data_ptr(), ext_nghbr.data_ptr(), B, V, poses.data_ptr(),
+                                              valid.data_ptr(), _stream(dev)), "magnet_relative_poses_f32")
     return poses, valid
 
 
@@ -277,6 +341,7 @@ def camera_rays(raw_intrinsics: torch.Tensor, H: int, W: int):
     B = raw_intrinsics.shape[0]
     intM = torch.empty(B, 3, 3, device=raw_intrinsics.device, dtype=torch.float32)
     rays = torch.empty(B, 3, H * W, device=raw_intrinsics.device, dtype=torch.float32)
-    check(lib().magnet_camera_rays_f32(raw_intrinsics.data_ptr(), B, H, W, intM.data_ptr(), rays.data_ptr(), _stream()),
-          "magnet_camera_rays_f32")
+    with torch.cuda.device(raw_intrinsics.device):
+        check(lib().magnet_camera_rays_f32(raw_intrinsics.data_ptr(), B, H, W, intM.data_ptr(), rays.data_ptr(),
+                                           _stream(raw_intrinsics.device)), "magnet_camera_rays_f32")
     return {"intM": intM, "unit_ray_array_2D": rays}

@@ -90,6 +90,42 @@ def cost_volume_cw(d_volume, ref_feat, nghbr_feat, ref_gmms, nghbr_gmms, R, t, i
     return volume / float(V)
 
 
+def cw_threshold_margin(d_volume, nghbr_gmms, R, t, is_valid, cam_intrins, thres):
+    """How close every output element is to a consistency-mask flip, on any device and at full size: min over the
+    valid views of | |z - mu~| - kappa*sigma~ | / max(|z|, kappa*sigma~, 1e-30) (the quantity magnet_oracle's
+    ``return_margin`` reports), with z, mu~, sigma~ produced by the same operators as cost_volume_cw above
+    (homography.py:130-158).  Used by the full-size parity tests: an element that differs from the reference by more
+    than the tolerance must have a margin below tests/util.MARGIN_TOL."""
+    B, D, H, W = d_volume.shape
+    V = int(nghbr_gmms.shape[0] / B)
+    n_mu, n_sigma = torch.split(nghbr_gmms, 1, dim=1)
+    dev = d_volume.device
+    margin = torch.full((B, D, H, W), float("inf"), device=dev, dtype=torch.float64)
+    for b in range(B):
+        K = cam_intrins['intM'][b, :, :].to(dev)
+        rays = cam_intrins['unit_ray_array_2D'][b, :, :].to(dev)
+        for v in range(V):
+            if is_valid[b, v].item() != 1:
+                continue
+            eye = torch.eye(3, device=dev)
+            cam_t = eye.matmul(t[b, v, :]).reshape(3, 1)
+            cam_r = eye.matmul(R[b, v, :, :]).matmul(rays)
+            pix_t = K.matmul(t[b, v, :]).reshape(3, 1)
+            pix_r = K.matmul(R[b, v, :, :]).matmul(rays)
+            src = v * B + b
+            d_rows = d_volume[b, ...].reshape(D, 1, -1)
+            grid = _sweep_grid(pix_t, pix_r, d_rows, H, W)
+            z_cam = (cam_t.unsqueeze(0) + cam_r.unsqueeze(0).repeat(D, 1, 1) * d_rows)[:, 2, :].reshape(D, H, W)
+            mu_w = _warp(n_mu[src, ...].unsqueeze(0).repeat(D, 1, 1, 1), grid)[:, 0]
+            sg_w = _warp(n_sigma[src, ...].unsqueeze(0).repeat(D, 1, 1, 1), grid)[:, 0]
+            gap, thr = torch.abs(z_cam - mu_w).double(), (sg_w * thres).double()
+            scale = torch.maximum(torch.maximum(z_cam.abs().double(), thr.abs()), torch.full_like(thr, 1e-30))
+            mg = (gap - thr).abs() / scale
+            mg = torch.where(torch.isfinite(mg), mg, torch.zeros_like(mg))
+            margin[b] = torch.minimum(margin[b], mg)
+    return margin
+
+
 def cost_volume_f(d_center, ref_feat, nghbr_feat, R, t, is_valid, cam_intrins, apply_softmax=True):
     """Fronto-parallel plane-sweep volume for F-Net training; same operator sequence as
     homography.est_costvolume_F (homography.py:10-75).  Differentiable in both feature maps."""

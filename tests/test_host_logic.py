@@ -152,3 +152,69 @@ def test_product_never_imports_the_oracle():
     for f in os.listdir(ROOT):
         if f.endswith(".py") and f not in allowed:
             assert not re.search(r"^\s*(from|import)\s+oracle\b", open(os.path.join(ROOT, f)).read(), re.M), f
+
+
+def test_packed_source_cache_hits_on_the_callers_tensor(monkeypatch):
+    """the repack must be keyed on the tensor object the caller passes — a `.detach()` temporary dies
+    before the next call and made every est_costvolume_CW call repack (157 MB at config 2).  Counted with mocked ops."""
+    from magnet_b200 import homography as hg, ops
+    calls = {"pixc": 0, "tiled": 0}
+
+    def fake_pixc(x, gmm=None, out=None):
+        calls["pixc"] += 1
+        return torch.zeros(1)
+
+    def fake_tiled(x, out=None):
+        calls["tiled"] += 1
+        return torch.zeros(1)
+
+    monkeypatch.setattr(ops, "repack_pixc", fake_pixc)
+    monkeypatch.setattr(ops, "repack_tiled32", fake_tiled)
+    hg.clear_cache()
+    feat, gmm = torch.zeros(4, 16, 3, 5), torch.zeros(4, 2, 3, 5)
+    for _ in range(3):                                       # the N_iter calls of one forward
+        _, layout = hg._packed_source(feat, gmm, 2, _lib.VARIANT_AUTO)
+        assert layout == _lib.SRC_PIXC
+    assert calls["pixc"] == 1
+    feat.add_(1.0)                                           # next forward writes new features in place
+    hg._packed_source(feat, gmm, 2, _lib.VARIANT_AUTO)
+    assert calls["pixc"] == 2
+    for _ in range(2):                                       # cross-check variants read TILED32, cached separately
+        _, layout = hg._packed_source(feat, gmm, 2, _lib.VARIANT_CELLS)
+        assert layout == _lib.SRC_TILED32
+    assert calls["tiled"] == 1
+    hg.prep_cache(False)
+    hg._packed_source(feat, gmm, 2, _lib.VARIANT_AUTO)
+    hg._packed_source(feat, gmm, 2, _lib.VARIANT_AUTO)
+    assert calls["pixc"] == 4                                # disabled: every call repacks
+    hg.prep_cache(True)
+    _, layout = hg._packed_source(torch.zeros(4, 20, 3, 5), None, 2, _lib.VARIANT_AUTO)
+    assert layout == _lib.SRC_TILED32                        # C = 20: not a PIXC channel count
+    hg.clear_cache()
+
+
+def test_camera_table_cache_tracks_both_pose_views(monkeypatch):
+    """t must be part of the key with its own base tensor and version, like R."""
+    from magnet_b200 import homography as hg, ops
+    n = {"c": 0}
+
+    def fake_pack(intM, R, t, valid):
+        n["c"] += 1
+        return torch.zeros(1)
+
+    monkeypatch.setattr(ops, "pack_cameras", fake_pack)
+    hg.clear_cache()
+    poses = torch.eye(4).repeat(2, 3, 1, 1)
+    cam = {"intM": torch.eye(3).repeat(2, 1, 1), "unit_ray_array_2D": torch.zeros(2, 3, 12)}
+    valid = torch.ones(2, 3, dtype=torch.int32)
+    dev = torch.device("cpu")
+    for _ in range(3):
+        hg._camera_table(cam, poses[:, :, :3, :3], poses[:, :, :3, 3], valid, dev)
+    assert n["c"] == 1
+    t_sep = poses[:, :, :3, 3].clone()                       # t allocated separately from R
+    hg._camera_table(cam, poses[:, :, :3, :3], t_sep, valid, dev)
+    assert n["c"] == 2
+    t_sep.add_(0.5)                                          # modified in place: must miss
+    hg._camera_table(cam, poses[:, :, :3, :3], t_sep, valid, dev)
+    assert n["c"] == 3
+    hg.clear_cache()

@@ -180,7 +180,10 @@ __device__ __forceinline__ void cell_list(const CostParams& p, const DepthSrc<MO
     const float inv_sg = MODE == MAGNET_DEPTH_GAUSS ? rcp_nr(ds.sg) : 1.0f;
     int jcur = j_lo;
     bool done = false;
+    int guard = 0;                                        // a step either records a cell, moves one grid line or ends:
+    const int guard_max = 2 * (W + H) + 2 * NCELLS + 64;   // more than any walk across the image can take
     while (__any_sync(FULL, !done)) {
+      if (++guard > guard_max && !done) { j_stop = jcur > j_lo ? jcur : j_lo + 1; done = true; }   // never spin, always advance
       if (!done) {
         const float dn = fminf(dX, dY);
         // first j in [jcur, jc_end) with depth_j >= dn  <=>  k_j >= kc
@@ -241,7 +244,9 @@ template <int MODE>
 __device__ __forceinline__ bool walk_ok(const CostParams& p, const DepthSrc<MODE>& ds, int jc, int jc_end, float a2,
                                         float q2) {
   if (MODE == MAGNET_DEPTH_VOLUME || p.k_sorted == 0) return false;
-  const bool sorted = MODE == MAGNET_DEPTH_PLANES ? true : (ds.sg > 0.0f && ds.sg < 1e30f && fabsf(ds.mu) < 1e30f);
+  // sigma must be a NORMAL positive number: rcp.approx.ftz of a denormal is inf, the crossing depths become NaN and
+  // the walk would never advance (a Gaussian update can shrink sigma by 1e-10 per iteration) -> exact walk instead
+  const bool sorted = MODE == MAGNET_DEPTH_PLANES ? true : (ds.sg >= 1e-30f && ds.sg < 1e30f && fabsf(ds.mu) < 1e30f);
   const float zA = __fadd_rn(a2, __fmul_rn(q2, depth_of<MODE>(p, ds, jc)));
   const float zB = __fadd_rn(a2, __fmul_rn(q2, depth_of<MODE>(p, ds, jc_end - 1)));
   return sorted && zA > 1e-6f && zB > 1e-6f && zA < 1e30f && zB < 1e30f;

@@ -38,15 +38,12 @@
 // (iii) bilinear polynomial instead of 4 explicit weights, (iv) fp32 view accumulation.  Each
 // changes results at the 1e-6 relative level; the hard consistency threshold can flip for elements
 // within ~1e-5 of it (the reference's own fp32-vs-fp64 flips have the same margins).
-#include <cstdlib>
+#include <mutex>
 
 #include "cells_common.cuh"
 
 namespace magnet {
 
-#ifndef MAGNET_DEFAULT_CTAS_PER_SM
-#define MAGNET_DEFAULT_CTAS_PER_SM 0
-#endif
 #ifndef MAGNET_NCELL
 #define MAGNET_NCELL 5
 #endif
@@ -256,40 +253,35 @@ cost_cells_kernel(const __grid_constant__ CostParams p, const int chunk, const i
 
 static int cells_grid_x(int H, int W) { return ((W + TILE_W - 1) / TILE_W) * ((H + TILE_H - 1) / TILE_H); }
 
-// Resident CTAs per SM are limited through the shared-memory carve-out so that the rest of the 228 KB
-// stays L1: the taps of neighbouring pixels / consecutive cells re-read the same source lines, and L1
-// only captures that when the CTAs' combined source footprint fits.  MAGNET_CTAS_PER_SM overrides.
-static int cells_carveout_pct(size_t smem_per_cta) {
-  int ctas = MAGNET_DEFAULT_CTAS_PER_SM;
-  if (const char* e = getenv("MAGNET_CTAS_PER_SM")) ctas = atoi(e);
-  if (ctas <= 0) return -1;                                   // leave the driver default
-  const size_t want = ctas * (smem_per_cta + 1024);           // 1 KB per-CTA reservation
-  int pct = (int)((want * 100 + 228 * 1024 - 1) / (228 * 1024));
-  return pct > 100 ? 100 : pct;
+// Opt-in shared memory size: set once per (kernel instantiation, device), not on every launch.
+template <typename K>
+static cudaError_t cells_attr_once(K kern, std::once_flag (&flags)[64]) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  cudaError_t res = cudaSuccess;
+  std::call_once(flags[dev & 63], [&] {
+    res = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cells_smem_bytes(MAGNET_MAX_PLANES));
+  });
+  return res;
+}
+
+template <int C, int MODE, bool CW, bool REUSE>
+static cudaError_t launch_cmw(const CostParams& p, cudaStream_t st) {
+  static std::once_flag flags[64];
+  auto kern = cost_cells_kernel<C, MODE, CW, REUSE>;
+  cudaError_t e = cells_attr_once(kern, flags);
+  if (e != cudaSuccess) return e;
+  const size_t smem = cells_smem_bytes(p.D);
+  const int chunk = cells_chunk(p.D), nchunks = (p.D + chunk - 1) / chunk;
+  dim3 grid(cells_grid_x(p.H, p.W) * nchunks, p.B), block(NT);
+  kern<<<grid, block, smem, st>>>(p, chunk, nchunks);
+  return cudaGetLastError();
 }
 
 template <int C, int MODE, bool REUSE>
 static cudaError_t launch_cm(const CostParams& p, bool cw, cudaStream_t st) {
-  const size_t smem = cells_smem_bytes(p.D);
-  const int chunk = cells_chunk(p.D), nchunks = (p.D + chunk - 1) / chunk;
-  const int grid_chunks = getenv("MAGNET_CHUNK_LOOP") ? 1 : nchunks;
-  dim3 grid(cells_grid_x(p.H, p.W) * grid_chunks, p.B), block(NT);
-  const int carve = cells_carveout_pct(smem);
-#define MAGNET_LAUNCH(CWv)                                                                              \
-  do {                                                                                                  \
-    auto kern = cost_cells_kernel<C, MODE, CWv, REUSE>;                                                 \
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e != cudaSuccess) return e;                                                                     \
-    if (carve > 0) {                                                                                    \
-      e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);            \
-      if (e != cudaSuccess) return e;                                                                   \
-    }                                                                                                   \
-    kern<<<grid, block, smem, st>>>(p, chunk, grid_chunks);                                                          \
-    return cudaGetLastError();                                                                          \
-  } while (0)
-  if (cw) MAGNET_LAUNCH(true);
-  MAGNET_LAUNCH(false);
-#undef MAGNET_LAUNCH
+  return cw ? launch_cmw<C, MODE, true, REUSE>(p, st) : launch_cmw<C, MODE, false, REUSE>(p, st);
 }
 
 template <int C>

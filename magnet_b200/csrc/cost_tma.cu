@@ -59,10 +59,10 @@ constexpr int OFF_BBOX = 16;                                 // int[2][4]  x_lo,
 constexpr int OFF_KS = 64;                                   // float[TCH] sampler offsets / plane depths of the chunk
 constexpr int OFF_CAM = OFF_KS + TCH * 4;                    // magnet_camera[TMAXV]
 constexpr int OFF_ORG = OFF_CAM + TMAXV * 64;                // float2[NORG][TPX]  cell origins
-constexpr int OFF_REC = OFF_ORG + NORG * TPX * 8;            // float4[3][NCP][TPX] records; the first 12 KB double as
-constexpr int OFF_WIN = ((OFF_REC + 3 * NCP * TPX * 16 + 127) / 128) * 128;   //   float2[4*KL][TPX] staging in phase A
+constexpr int OFF_REC = OFF_ORG + NORG * TPX * 8;            // float4[3][NCP][TPX] records; every warp's own rows double
+constexpr int OFF_WIN = ((OFF_REC + 3 * NCP * TPX * 16 + 127) / 128) * 128;   //   as its float2 staging slots in phase A
 constexpr int TMA_SMEM_TOTAL = (228 * 1024 - 2 * 1024) / 2;  // two CTAs per SM (1 KB per CTA is reserved by the driver)
-static_assert(4 * KL * TPX * 8 <= 3 * NCP * TPX * 16, "staging must fit inside the record array");
+static_assert(4 * KL <= 3 * NCP, "one staging slot per record row (see phase_a)");
 static_assert(OFF_CAM % 16 == 0 && OFF_ORG % 16 == 0 && OFF_REC % 16 == 0, "alignment");
 
 __host__ __device__ constexpr int pix_floats(int C) { return C + 4; }
@@ -135,7 +135,11 @@ __device__ __forceinline__ LaneCells phase_a(const ViewGeom& g, const uint32_t t
   unsigned mask = 0u;
   int k = 0;
   float pcx = 0.0f, pcy = 0.0f;
-  float2* mystg = stg + (h * KL) * TPX + pxl;
+  // staging slot (h, k) of pixel p lives in the first half of the 128-byte segment that record row h*KL + k holds for
+  // this warp's 8 pixels: staging never touches bytes that belong to another warp's records (which that warp may
+  // still be reading in phase C of the previous view)
+  float2* mystg = stg + ((h * KL) * TPX + (pxl & ~7)) * 2 + (lane & 7);
+  constexpr int SK = 2 * TPX;                             // float2 stride between consecutive staging slots
 #pragma unroll 1
   for (int m = 0; m < mend; m += 2) {
     float d0, d1;
@@ -149,12 +153,12 @@ __device__ __forceinline__ LaneCells phase_a(const ViewGeom& g, const uint32_t t
     const bool f0 = (m >= mlo) && ((x0 != pcx) || (y0 != pcy) || m == mlo);
     const bool f1 = (m + 1 >= mlo) && ((x1 != x0) || (y1 != y0) || m + 1 == mlo);
     if (f0) {
-      if (k < KL) mystg[k * TPX] = make_float2(x0, y0);
+      if (k < KL) mystg[k * SK] = make_float2(x0, y0);
       ++k;
       mask |= 1u << m;
     }
     if (f1) {
-      if (k < KL) mystg[k * TPX] = make_float2(x1, y1);
+      if (k < KL) mystg[k * SK] = make_float2(x1, y1);
       ++k;
       mask |= 2u << m;
     }
@@ -206,7 +210,7 @@ __device__ __forceinline__ LaneCells phase_a(const ViewGeom& g, const uint32_t t
   for (int kk = 0; kk < KL; ++kk) {
     const int gi = kk - skip;
     if (gi >= 0 && gi < n) {
-      const float2 o = mystg[kk * TPX];
+      const float2 o = mystg[kk * SK];
       org[(base + gi) * TPX + pxl] = o;
       bx_lo = fminf(bx_lo, o.x); bx_hi = fmaxf(bx_hi, o.x);
       by_lo = fminf(by_lo, o.y); by_hi = fmaxf(by_hi, o.y);
@@ -664,7 +668,12 @@ static cudaError_t launch_tma_cmw(const CostParams& p, cudaStream_t st) {
   const int nchunks = (p.D + TCH - 1) / TCH;
   const int tiles = ((p.W + TTW - 1) / TTW) * ((p.H + TTH - 1) / TTH);
   dim3 grid(tiles * nchunks, p.B), block(TNT);
-  kern<<<grid, block, TMA_SMEM_TOTAL, st>>>(p, tm, tma_win_cap(C), nchunks);
+#ifdef MAGNET_TMA_FORCE_GLOBAL   // debug build: never stage a window (all taps through the global-memory path)
+  const int cap = 0;
+#else
+  const int cap = tma_win_cap(C);
+#endif
+  kern<<<grid, block, TMA_SMEM_TOTAL, st>>>(p, tm, cap, nchunks);
   return cudaGetLastError();
 }
 

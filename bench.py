@@ -264,7 +264,7 @@ def main():
     is_valid_d = inp.is_valid.to(dev)
     intM_d = inp.cam_intrins['intM'].to(dev)
     rays_d = inp.cam_intrins['unit_ray_array_2D'].to(dev).contiguous()
-    pixc = variant in (_lib.VARIANT_AUTO, _lib.VARIANT_TMA)           # production layout; the cross-check kernels read TILED32
+    pixc = variant == _lib.VARIANT_TMA                               # TMA-staged kernel: PIXC; global-gather kernels: TILED32
     layout = _lib.SRC_PIXC if pixc else _lib.SRC_TILED32
     src_packed = (torch.empty(V * B, H, Wd, C + 4, device=dev) if pixc
                   else torch.empty(V * B, H, (Wd + 31) // 32, C // 4, 32, 4, device=dev))
@@ -475,8 +475,9 @@ def main():
     grid, block, smem = ops.cost_launch_info(B, V, D, C, H, Wd, variant=_lib.VARIANT_CELLS if variant == _lib.VARIANT_CELLS_NOREUSE else variant)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(args.config), "kernel": {_lib.VARIANT_DIRECT: "cost_direct_kernel<CW>", _lib.VARIANT_CELLS: "cost_cells_kernel<64,GAUSS,CW> (TILED32 gather)",
-                           _lib.VARIANT_CELLS_NOREUSE: "cost_cells_kernel<64,GAUSS,CW,noreuse>"}.get(
-                               variant, "cost_tma_kernel<64,GAUSS,CW> (PIXC layout, TMA-staged window)"),
+                           _lib.VARIANT_CELLS_NOREUSE: "cost_cells_kernel<64,GAUSS,CW,noreuse>",
+                           _lib.VARIANT_TMA: "cost_tma_kernel<64,GAUSS,CW> (PIXC layout, TMA-staged window)"}.get(
+                               variant, "cost_cells_kernel<64,GAUSS,CW> (TILED32 gather)"),
                 "kernel_ms_how": "CUDA events around every cost-kernel launch of %d eager steps run right after the "
                                  "graph-replayed timed region (same kernels, arguments and buffers)" % min(K, 50),
                 "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src,

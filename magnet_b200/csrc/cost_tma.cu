@@ -119,8 +119,11 @@ struct LaneCells {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// Phase A: hypotheses >= jlo of the pixel are pending.  TMEM columns tm + 4p .. 4p+1 hold my depths 2p, 2p+1;
+// Phase A: hypotheses >= jlo of the pixel are pending.  TMEM columns tm + 8q .. 8q+3 hold my depths 4q .. 4q+3;
 // depths beyond my last hypothesis replicate it (so they never start a cell and need no predicate).
+// Every lane projects each of its hypotheses and records the changes of cell: exact for any depth order and sign of z.
+// (The analytic grid-line walk of cost_cells.cu was tried here over each lane's quarter of the hypotheses: with 32
+// lanes walking in lockstep and a binary search per step it measured 6 % SLOWER than this loop — profiles/r2_*.md.)
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ LaneCells phase_a(const ViewGeom& g, const uint32_t tm, const int mend, const int nj,
                                              const int jb, const int jlo, const int Dc, const int W, const int H,
@@ -134,41 +137,54 @@ __device__ __forceinline__ LaneCells phase_a(const ViewGeom& g, const uint32_t t
   __syncwarp();                                           // the staging area aliases the records phase C just read
   unsigned mask = 0u;
   int k = 0;
+  int lane_stop = nj;                                     // first of MY hypotheses that this walk does not cover
   float pcx = 0.0f, pcy = 0.0f;
   // staging slot (h, k) of pixel p lives in the first half of the 128-byte segment that record row h*KL + k holds for
   // this warp's 8 pixels: staging never touches bytes that belong to another warp's records (which that warp may
   // still be reading in phase C of the previous view)
   float2* mystg = stg + ((h * KL) * TPX + (pxl & ~7)) * 2 + (lane & 7);
   constexpr int SK = 2 * TPX;                             // float2 stride between consecutive staging slots
+  {
 #pragma unroll 1
-  for (int m = 0; m < mend; m += 2) {
-    float d0, d1;
-    tmem_ld2(tm + 2 * m, d0, d1);
-    float2 ix, iy, z;
-    project2(make_float2(d0, d1), g, ix, iy, z);
-    // anything left of -1 / right of W (above / below likewise) has all four taps out of the image: clamp so that
-    // cell coordinates stay small and NaN (fmaxf drops it) maps to "out of bounds"
-    const float x0 = floorf(fminf(fmaxf(ix.x, -2.0f), xmax)), y0 = floorf(fminf(fmaxf(iy.x, -2.0f), ymax));
-    const float x1 = floorf(fminf(fmaxf(ix.y, -2.0f), xmax)), y1 = floorf(fminf(fmaxf(iy.y, -2.0f), ymax));
-    const bool f0 = (m >= mlo) && ((x0 != pcx) || (y0 != pcy) || m == mlo);
-    const bool f1 = (m + 1 >= mlo) && ((x1 != x0) || (y1 != y0) || m + 1 == mlo);
-    if (f0) {
-      if (k < KL) mystg[k * SK] = make_float2(x0, y0);
-      ++k;
-      mask |= 1u << m;
+    for (int m = 0; m < mend; m += 4) {                   // 4 hypotheses per trip: two independent packed projections
+      float d0, d1, d2, d3;
+      tmem_ld4(tm + 2 * m, d0, d1, d2, d3);
+      float2 ixa, iya, za, ixb, iyb, zb;
+      project2(make_float2(d0, d1), g, ixa, iya, za);
+      project2(make_float2(d2, d3), g, ixb, iyb, zb);
+      // anything left of -1 / right of W (above / below likewise) has all four taps out of the image: clamp so that
+      // cell coordinates stay small and NaN (fmaxf drops it) maps to "out of bounds"
+      float cx[4], cy[4];
+      cx[0] = floorf(fminf(fmaxf(ixa.x, -2.0f), xmax)); cy[0] = floorf(fminf(fmaxf(iya.x, -2.0f), ymax));
+      cx[1] = floorf(fminf(fmaxf(ixa.y, -2.0f), xmax)); cy[1] = floorf(fminf(fmaxf(iya.y, -2.0f), ymax));
+      cx[2] = floorf(fminf(fmaxf(ixb.x, -2.0f), xmax)); cy[2] = floorf(fminf(fmaxf(iyb.x, -2.0f), ymax));
+      cx[3] = floorf(fminf(fmaxf(ixb.y, -2.0f), xmax)); cy[3] = floorf(fminf(fmaxf(iyb.y, -2.0f), ymax));
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int mm = m + e;
+        const float qx = e ? cx[e - 1] : pcx, qy = e ? cy[e - 1] : pcy;
+        const bool f = (mm >= mlo) && ((cx[e] != qx) || (cy[e] != qy) || mm == mlo);
+        if (f) {
+          if (k < KL) mystg[k * SK] = make_float2(cx[e], cy[e]);
+          ++k;
+          mask |= 1u << mm;
+        }
+      }
+      pcx = cx[3];
+      pcy = cy[3];
     }
-    if (f1) {
-      if (k < KL) mystg[k * SK] = make_float2(x1, y1);
-      ++k;
-      mask |= 2u << m;
+    if (__any_sync(FULL, k > KL)) {                       // more cells than staging slots: cover up to the first unsaved
+      if (k > KL) {
+        lane_stop = (int)__fns(mask, 0, KL + 1);
+        mask &= (1u << lane_stop) - 1u;
+        k = KL;
+      }
     }
-    pcx = x1;
-    pcy = y1;
   }
   // ---- splice the four lists of the pixel --------------------------------------------------------------------
   const bool has = mlo < TJL;
   const float plx = __shfl_up_sync(FULL, pcx, 8), ply = __shfl_up_sync(FULL, pcy, 8);   // last cell of lane h-1
-  const float2 first = has ? mystg[0] : make_float2(0.f, 0.f);
+  const float2 first = (has && k > 0) ? mystg[0] : make_float2(-1e9f, -1e9f);
   // my first pending hypothesis continues the cell of the previous lane's last hypothesis (which is pending, too)
   const bool cont = has && h > 0 && mlo == 0 && jb > jlo && first.x == plx && first.y == ply;
   const int skip = cont ? 1 : 0;
@@ -183,16 +199,16 @@ __device__ __forceinline__ LaneCells phase_a(const ViewGeom& g, const uint32_t t
     incl = s;
   };
   int incl;
-  const int kept_l = min(n, KL - skip);                   // staging holds KL entries, the skipped first included
-  scan4(kept_l, incl);
-  int base = incl - kept_l;
-  const int kept_g = max(0, min(kept_l, NORG - base));
+  scan4(n, incl);
+  int base = incl - n;
+  const int kept_g = max(0, min(n, NORG - base));
   int jstop = Dc;
   complete = true;
-  if (__any_sync(FULL, kept_g < n)) {                     // some lane of the warp has to drop cells: rare
+  if (__any_sync(FULL, kept_g < n || lane_stop < nj)) {   // some lane of the warp has to drop cells: rare
     complete = false;                                     // (dropped cells are not in the bounding box)
     int js = Dc;
     if (kept_g < n) js = jb + (int)__fns(mask, 0, kept_g + 1);   // my first dropped start
+    else if (lane_stop < nj) js = jb + lane_stop;
     js = min(js, __shfl_xor_sync(FULL, js, 8));
     js = min(js, __shfl_xor_sync(FULL, js, 16));
     jstop = js;
@@ -339,7 +355,7 @@ __device__ __forceinline__ void phase_b(const float2 (&ref2)[C / 8], const int n
 
 // ---------------------------------------------------------------------------------------------------------------
 // Phase C: every lane evaluates its pending hypotheses whose cell index lies in [i0, i0 + NCP) from the records and
-// adds them to its accumulators (TMEM columns tm + 4p + 2, + 3).
+// adds them to its accumulators (TMEM columns tm + 8q + 4 .. 8q + 7).
 // ---------------------------------------------------------------------------------------------------------------
 template <bool CW>
 __device__ __forceinline__ void phase_c(const ViewGeom& g, const uint32_t tm, const int mend, const LaneCells& lc,
@@ -353,13 +369,14 @@ __device__ __forceinline__ void phase_c(const ViewGeom& g, const uint32_t tm, co
   int cur = -1000;                                        // at the cell lane h-1 ended in; cur = the one loaded
   unsigned msk = lc.mask;
 #pragma unroll 1
-  for (int m = 0; m < mend; m += 2) {
-    float d0, d1, a0, a1;
-    tmem_ld4(tm + 2 * m, d0, d1, a0, a1);
-    float2 ix, iy, z;
-    project2(make_float2(d0, d1), g, ix, iy, z);
+  for (int m = 0; m < mend; m += 4) {                     // 4 hypotheses per trip (instruction-level parallelism)
+    float v[8];                                           // my depths m..m+3 and their accumulators
+    tmem_ld8(tm + 2 * m, v);
+    float2 ix2[2], iy2[2], z2[2];
+    project2(make_float2(v[0], v[1]), g, ix2[0], iy2[0], z2[0]);
+    project2(make_float2(v[2], v[3]), g, ix2[1], iy2[1], z2[1]);
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
+    for (int e = 0; e < 4; ++e) {
       const int mm = m + e;
       cnt += (int)(msk & 1u);
       msk >>= 1;
@@ -374,7 +391,9 @@ __device__ __forceinline__ void phase_c(const ViewGeom& g, const uint32_t tm, co
         lds128_if(st, rec_a + ro + (uint32_t)(NCP * TPX * 16), rm);
         lds128_if(st, rec_a + ro + (uint32_t)(2 * NCP * TPX * 16), rs);
       }
-      const float fx = (e ? ix.y : ix.x) - ox, fy = (e ? iy.y : iy.x) - oy;
+      const float pxi = (e & 1) ? ix2[e >> 1].y : ix2[e >> 1].x, pyi = (e & 1) ? iy2[e >> 1].y : iy2[e >> 1].x;
+      const float pz = (e & 1) ? z2[e >> 1].y : z2[e >> 1].x;
+      const float fx = pxi - ox, fy = pyi - oy;
       const float cost = __fmaf_rn(fy, __fmaf_rn(fx, rd.w, rd.z), __fmaf_rn(fx, rd.y, rd.x));
       bool ok;
       if (CW) {
@@ -382,14 +401,13 @@ __device__ __forceinline__ void phase_c(const ViewGeom& g, const uint32_t tm, co
         const float sg = __fmaf_rn(fy, __fmaf_rn(fx, rs.w, rs.z), __fmaf_rn(fx, rs.y, rs.x));
         // homography.py:157-158: |z - mu~| < sigma~ * kappa, strict.  A non-finite position makes mu~ NaN (0 * inf),
         // the comparison false and the contribution 0 — what the reference's +-10 clamp + zero padding produce.
-        ok = fabsf(__fsub_rn(e ? z.y : z.x, mu)) < __fmul_rn(sg, kappa);
+        ok = fabsf(__fsub_rn(pz, mu)) < __fmul_rn(sg, kappa);
       } else {
         ok = fabsf(cost) < 3.0e38f;                       // all-zero record x non-finite position
       }
-      const float add = (ok && inr) ? cost : 0.0f;
-      if (e) a1 += add; else a0 += add;
+      v[4 + e] += (ok && inr) ? cost : 0.0f;
     }
-    tmem_st2(tm + 2 * m + 2, a0, a1);
+    tmem_st4(tm + 2 * m + 4, v[4], v[5], v[6], v[7]);
   }
   tmem_wait_st();
 }
@@ -420,7 +438,7 @@ cost_tma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
   const int jc = (blockIdx.x % nchunks) * TCH;
   const int Dc = min(TCH, D - jc);
   const int JLc = (Dc + 3) >> 2;                           // hypotheses per lane in this chunk
-  const int mend = (JLc + 1) & ~1;                         // ... rounded up to whole pairs (CTA-uniform loop bound)
+  const int mend = (JLc + 3) & ~3;                         // ... rounded up to whole quads (CTA-uniform loop bound)
   const int jb = h * JLc;                                  // my first (chunk-local) hypothesis
   const int nj = min(max(Dc - jb, 0), JLc);                // how many I own
   const int trow = warp >> 1, tcol = (warp & 1) * 8 + (lane & 7);
@@ -445,7 +463,7 @@ cost_tma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
     mbar_arrive_expect_tx(bar, (uint32_t)V * 64u);
     bulk_load(smem_u32(smem + OFF_CAM), p.cams + (size_t)b * V, (uint32_t)V * 64u, bar);
   }
-  // my TMEM window: lanes 32*(warp%4).., 32 columns per warp group; column 4p+{0,1} depths, 4p+{2,3} accumulators
+  // my TMEM window: lanes 32*(warp%4).., 32 columns per warp group; columns 8q+{0..3} depths, 8q+{4..7} accumulators
   const uint32_t tmem_base = *reinterpret_cast<const volatile uint32_t*>(smem + OFF_TMEM);
   const uint32_t tm = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 32);
 
@@ -466,10 +484,10 @@ cost_tma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
       sg = ldg_f(p.ref_gmm + ((size_t)b * 2 + 1) * HW + n);
     }
 #pragma unroll 1
-    for (int m = 0; m < mend; m += 2) {
-      float d[2];
+    for (int m = 0; m < mend; m += 4) {
+      float d[4];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
+      for (int e = 0; e < 4; ++e) {
         const int j = jb + min(m + e, max(nj - 1, 0));     // tail replicates my last hypothesis (never starts a cell)
         float v = 0.0f;
         if (nj > 0) {
@@ -479,7 +497,8 @@ cost_tma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
         }
         d[e] = v;
       }
-      tmem_st4(tm + 2 * m, d[0], d[1], 0.0f, 0.0f);
+      tmem_st4(tm + 2 * m, d[0], d[1], d[2], d[3]);
+      tmem_st4(tm + 2 * m + 4, 0.0f, 0.0f, 0.0f, 0.0f);
     }
     tmem_wait_st();
   }
@@ -520,15 +539,20 @@ cost_tma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
     const int row_bytes = nxb * BOX;
     const int cbase = OFF_WIN + h * QL * 16 - (wy0 * row_bytes + wx0 * PS);
     if (staged) {
-      if (warp == 0) {
-        const int nops = nxb * wh;
-        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)nops * BOX);
-        __syncwarp();
-        for (int op = lane; op < nops; op += 32) {
-          const int r = op / nxb, xb = op - r * nxb;
+      // one elected lane per warp issues its share of the 8-pixel boxes (uniform-datapath instructions: a per-lane
+      // loop would be serialised by the compiler anyway); thread 0 arms the barrier with the byte count — the
+      // transaction count may run negative until then, the phase cannot complete before the arrival
+      const int nops = nxb * wh;
+      if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)nops * BOX);
+      if (lane == 0) {
+        int r = warp / nxb, xb = warp - r * nxb;
+        for (int op = warp; op < nops; op += TNT / 32) {
           tma_load_4d(smem_u32(win) + (uint32_t)op * BOX, &tmap, bar, 0, wx0 + 8 * xb, wy0 + r, vb);
+          xb += TNT / 32;
+          while (xb >= nxb) { xb -= nxb; ++r; }
         }
       }
+      __syncwarp();
       mbar_wait(bar, phase);
       phase ^= 1u;
     }
@@ -557,11 +581,12 @@ cost_tma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
     float* outp = p.out + ((size_t)b * D + jc + jb) * HW + n;
     const bool exact = p.inv_v_exact != 0.0f;              // V a power of two: the division is an exact scaling
 #pragma unroll 1
-    for (int m = 0; m < mend; m += 2) {
-      float d0, d1, a0, a1;
-      tmem_ld4(tm + 2 * m, d0, d1, a0, a1);
-      if (live && m < nj) outp[(size_t)m * HW] = exact ? a0 * p.inv_v_exact : __fdiv_rn(a0, p.vf);
-      if (live && m + 1 < nj) outp[(size_t)(m + 1) * HW] = exact ? a1 * p.inv_v_exact : __fdiv_rn(a1, p.vf);
+    for (int m = 0; m < mend; m += 4) {
+      float a[4];
+      tmem_ld4(tm + 2 * m + 4, a[0], a[1], a[2], a[3]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (live && m + e < nj) outp[(size_t)(m + e) * HW] = exact ? a[e] * p.inv_v_exact : __fdiv_rn(a[e], p.vf);
     }
   }
   tmem_fence_before_sync();

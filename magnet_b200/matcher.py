@@ -58,7 +58,7 @@ class MatchingPlan:
     device intrinsics / rays, camera-constant table, source features in the gather layout."""
 
     def __init__(self, ref_feat, nghbr_feat, nghbr_gmms, nghbr_poses, is_valid, cam_intrins, *,
-                 thres: int = 5, src_layout: int = _lib.SRC_PIXC):
+                 thres: int = 5, src_layout: int = _lib.SRC_TILED32):
         dev = ref_feat.device
         self.B, self.C, self.H, self.W = ref_feat.shape
         self.V = nghbr_feat.shape[0] // self.B
@@ -71,6 +71,8 @@ class MatchingPlan:
         self.cams = ops.pack_cameras(intM, R, t, is_valid.to(dev, torch.int32))
         self._nghbr_feat = nghbr_feat.detach()
         self._packed = {}
+        # Sampler-fused loop: the global-gather kernel (TILED32) is the faster one at every measured size (profiles/
+        # r2_kernels.md); pass src_layout=SRC_PIXC / variant=VARIANT_TMA for the TMA-staged kernel.
         if src_layout == _lib.SRC_PIXC and not (self.C in (16, 32, 64) and self.V <= 16):
             src_layout = _lib.SRC_TILED32
         if src_layout == _lib.SRC_TILED32 and self.C % 4 != 0:
@@ -92,8 +94,10 @@ class MatchingPlan:
     def cost(self, gmm: torch.Tensor, k, out: Optional[torch.Tensor] = None, variant=_lib.VARIANT_AUTO):
         """Fused sampler + CW cost volume for the current Gaussian (B,2,H,W)."""
         layout = self.layout
-        if variant in (_lib.VARIANT_DIRECT, _lib.VARIANT_CELLS, _lib.VARIANT_CELLS_NOREUSE) and layout == _lib.SRC_PIXC:
-            layout = _lib.SRC_TILED32                      # the cross-check kernels gather from TILED32
+        if variant == _lib.VARIANT_TMA:
+            layout = _lib.SRC_PIXC                         # the TMA-staged kernel fetches its windows from PIXC
+        elif layout == _lib.SRC_PIXC and variant in (_lib.VARIANT_DIRECT, _lib.VARIANT_CELLS, _lib.VARIANT_CELLS_NOREUSE):
+            layout = _lib.SRC_TILED32                      # the global-gather kernels read TILED32
         return ops.cost_volume(self.ref_feat, self._source(layout), self.rays, self.cams, V=self.V, src_layout=layout,
                                consistency=True, src_gmm=self.src_gmm, kappa=self.kappa, ref_gmm=gmm.detach(),
                                k=k, out=out, variant=variant)

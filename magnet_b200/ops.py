@@ -236,7 +236,7 @@ def cost_launch_info(B, V, D, Cc, H, W, variant=_lib.VARIANT_AUTO):
     """(grid CTAs, threads per CTA, dynamic smem bytes) the cost kernel would use for these sizes."""
     a = CostArgs()
     a.B, a.V, a.D, a.C, a.H, a.W = B, V, D, Cc, H, W
-    layout = _lib.SRC_PIXC if variant in (_lib.VARIANT_AUTO, _lib.VARIANT_TMA) else _lib.SRC_TILED32
+    layout = _lib.SRC_PIXC if variant == _lib.VARIANT_TMA else _lib.SRC_TILED32
     a.depth_mode, a.src_layout, a.consistency, a.variant = _lib.DEPTH_PLANES, layout, 0, variant
     one = C.c_void_p(0x1000)                       # never dereferenced: validated for non-NULL / alignment only
     a.ref_feat = a.src_feat = a.rays = a.cams = a.out = a.k_host = one

@@ -1,5 +1,5 @@
-"""Kernel-only timing of the fused cost kernel (fused sampler mode) for quick A/B runs on the GPU box.
-usage: [MAGNET_B200_LIB=...] [MAGNET_CTAS_PER_SM=n] python scripts/kbench.py [cfg2|cfg3] [variant] [reps]"""
+"""Kernel-only timing of the cost kernel for quick A/B runs on the GPU box.
+usage: [MAGNET_B200_LIB=...] python scripts/kbench.py [cfg2|cfg3] [variant] [reps] [gauss|volume]   (volume = drop-in d_volume mode)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -9,20 +9,33 @@ from magnet_b200.synthetic import make_config
 cfg = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 variant = {"auto": 0, "direct": 1, "cells": 2, "noreuse": 3, "tma": 4}[(sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] else "auto")]
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+mode = sys.argv[4] if len(sys.argv) > 4 else "gauss"
 inp = make_config(cfg, seed=1)
 g = inp.to("cuda")
 plan = magnet_b200.MatchingPlan(g.ref_feat, g.nghbr_feat, g.nghbr_gmms, g.nghbr_poses, inp.is_valid, inp.cam_intrins, thres=5)
 k = ops.k_array(inp.k.tolist())
 out = torch.empty(inp.B, inp.D, *inp.ref_feat.shape[2:], device="cuda")
 flush = torch.empty(64 * 1024 * 1024, device="cuda")     # 256 MB > L2
+dvol = ops.sample_depths(g.ref_gmms, k) if mode == "volume" else None
+
+
+def launch():
+    if dvol is None:
+        plan.cost(g.ref_gmms, k, out=out, variant=variant)
+    else:
+        layout = _lib.SRC_PIXC if variant == 4 else _lib.SRC_TILED32
+        ops.cost_volume(plan.ref_feat, plan._source(layout), plan.rays, plan.cams, V=plan.V, src_layout=layout, consistency=True,
+                        src_gmm=plan.src_gmm, kappa=plan.kappa, d_volume=dvol, out=out, variant=variant)
+
+
 for _ in range(3):
-    plan.cost(g.ref_gmms, k, out=out, variant=variant)
+    launch()
 ts = []
 for _ in range(reps):
     flush.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); plan.cost(g.ref_gmms, k, out=out, variant=variant); e1.record()
+    e0.record(); launch(); e1.record()
     torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
 ts.sort()
-print("%s lib=%s ctas=%s variant=%s: median %.4f ms  min %.4f ms" % (cfg, os.path.basename(os.environ.get("MAGNET_B200_LIB", "default")),
-      os.environ.get("MAGNET_CTAS_PER_SM", "-"), variant, ts[len(ts) // 2], ts[0]))
+print("%s lib=%s mode=%s variant=%s: median %.4f ms  min %.4f ms" % (cfg, os.path.basename(os.environ.get("MAGNET_B200_LIB", "default")),
+      mode, variant, ts[len(ts) // 2], ts[0]))

@@ -67,11 +67,11 @@ def test_cost_args_validation_without_gpu():
 
 def test_launch_info_matches_design():
     from magnet_b200 import ops
-    grid, block, smem = ops.cost_launch_info(8, 4, 64, 64, 120, 160)     # AUTO -> TMA-staged kernel (PIXC layout)
+    grid, block, smem = ops.cost_launch_info(8, 4, 64, 64, 120, 160, variant=_lib.VARIANT_TMA)   # TMA-staged kernel
     assert (grid, block) == (8 * 10 * 30, 256)                          # 16 x 4 pixel tiles x 4 lanes, one chunk of 64
     assert smem == (228 * 1024 - 2 * 1024) // 2                         # two CTAs per SM
     assert ops.cost_launch_info(8, 4, 256, 64, 120, 160, variant=_lib.VARIANT_TMA)[0] == 8 * 10 * 30 * 4
-    grid, block, smem = ops.cost_launch_info(8, 4, 64, 64, 120, 160, variant=_lib.VARIANT_CELLS)
+    grid, block, smem = ops.cost_launch_info(8, 4, 64, 64, 120, 160)     # AUTO (TILED32) -> global-gather kernel
     assert (grid, block) == (8 * 10 * 15 * 2, 128)                      # 16 x 8 pixel tiles x 2 chunks of 32 planes
     assert smem == 5 * 3 * 128 * 16 + 5 * 128 * 8 + 32 * 128 * 4 + 32 * 4    # 5 records + headers + chunk + k
     grid, block, smem = ops.cost_launch_info(8, 4, 64, 64, 120, 160, variant=_lib.VARIANT_DIRECT)

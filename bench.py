@@ -15,8 +15,9 @@ scaling (each rank owns its own batch of 8; the path has no data-path collective
             timed region
   roofline  dominant kernel (cost volume): algorithmic bytes / its CUDA-event duration vs measured HBM peak
   cpu_baseline / --impl reference
-            the reference's CPU path (its ATen operator sequence, oracle/torch_ref.py — /root/reference is a
-            Python repo and cannot travel) timed on this box's host cores on a bounded sample (1-frame batches)
+            the reference's CPU path — the unmodified est_costvolume_CW from the vendored baseline/_ref (git-ignored copy of
+            /root/reference made by scripts/vendor_ref.sh; travels with the snapshot), else its bit-identical ATen port —
+            timed on this box's host cores on a bounded sample (1-frame batches)
 """
 import argparse
 import json
@@ -155,11 +156,26 @@ def pin_to_gpu_cpus(index):
     return None
 
 
+def reference_ops():
+    """The reference's cost-volume function for the baseline legs: the UNMODIFIED models.submodules.homography
+    .est_costvolume_CW (from /root/reference, or its vendored copy baseline/_ref made by scripts/vendor_ref.sh) when
+    available — kind "reference" — else its bit-identical ATen port oracle/torch_ref.py — kind "port".  The sampler
+    (MAGNET.py:154-156) and the update (MAGNET.py:60-69) are inlined in the reference's forward; they are issued here as
+    the same ATen expressions (oracle/torch_ref.py)."""
+    from oracle import torch_ref
+    from oracle.ref_loader import load_reference
+    ref = load_reference()
+    if ref is not None:
+        return ref.homography.est_costvolume_CW, "reference", ref.root
+    return torch_ref.cost_volume_cw, "port", "oracle/torch_ref.py"
+
+
 def cpu_reference_frames(frames_cfg, steps, warmup, threads=None, budget_s=None):
-    """Time the reference's CPU operator sequence (oracle/torch_ref.py: sampler -> est_costvolume_CW ->
-    Gaussian update, N_ITER iterations) on 1-frame batches of the same workload.  Returns (frames/s, info)."""
+    """Time the reference's CPU path (sampler -> est_costvolume_CW -> Gaussian update, N_ITER iterations) on 1-frame
+    batches of the same workload.  Returns (frames/s, info)."""
     from magnet_b200.synthetic import make_config
     from oracle import torch_ref
+    cost_fn, kind, where = reference_ops()
     # torchrun exports OMP_NUM_THREADS=1; the CPU arm must use every host core it may run on.  One thread per
     # PHYSICAL core (what torch picks by default): 128 threads on the 64-core / 128-thread GPU host were
     # measured 8x slower than 64 (oversubscribed hyper-threads).
@@ -183,8 +199,8 @@ def cpu_reference_frames(frames_cfg, steps, warmup, threads=None, budget_s=None)
         pred = inp.ref_gmms
         for _ in range(N_ITER):
             dvol = torch_ref.sample_depth_candidates(pred, klist)
-            torch_ref.cost_volume_cw(dvol, inp.ref_feat, inp.nghbr_feat, inp.ref_gmms, inp.nghbr_gmms, inp.R, inp.t,
-                                     inp.is_valid, inp.cam_intrins, inp.thres)
+            cost_fn(dvol, inp.ref_feat, inp.nghbr_feat, inp.ref_gmms, inp.nghbr_gmms, inp.R, inp.t,
+                    inp.is_valid, inp.cam_intrins, inp.thres)
             pred = torch_ref.gaussian_update(raw, pred)
         return pred
 
@@ -199,9 +215,11 @@ def cpu_reference_frames(frames_cfg, steps, warmup, threads=None, budget_s=None)
             if budget_s is not None and time.perf_counter() - t0 > budget_s:
                 break
         dt = time.perf_counter() - t0
-    info = {"cores": cores, "os_cpu_count": os.cpu_count(), "frames": done, "seconds": dt,
+    what = ("unmodified models.submodules.homography.est_costvolume_CW (%s)" % where if kind == "reference"
+            else "ATen port of the reference operator sequence (%s)" % where)
+    info = {"cores": cores, "os_cpu_count": os.cpu_count(), "frames": done, "seconds": dt, "kind": kind,
             "sample": f"{done} x 1-frame batch of {WORKLOADS[frames_cfg]} (B=1), {N_ITER} iterations each, "
-                      f"ATen port of the reference operator sequence, {cores} threads"}
+                      f"{what}, {cores} threads"}
     return done / dt, info
 
 
@@ -214,7 +232,7 @@ def run_reference_arm(args, rank):
         "steps": info["frames"], "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * info["seconds"] / max(1, info["frames"]),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.config], "n_iter": N_ITER, "device": "host CPU"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -486,14 +504,14 @@ def main():
     # grid_sample, mul, sum ... — ATen port, bit-identical to the reference on CPU) on the same B200, same inputs
     reference_cuda = None
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import torch_ref
+        ref_cost_fn, ref_kind, _ = reference_ops()
         torch.backends.cuda.matmul.allow_tf32 = False
         dvol_ref = ops.sample_depths(g.ref_gmms, karr)
         cam_dev = {"intM": intM_d, "unit_ray_array_2D": rays_d}
 
         def ref_call():
-            return torch_ref.cost_volume_cw(dvol_ref, g.ref_feat, g.nghbr_feat, g.ref_gmms, g.nghbr_gmms, g.R, g.t,
-                                            inp.is_valid, cam_dev, inp.thres)
+            return ref_cost_fn(dvol_ref, g.ref_feat, g.nghbr_feat, g.ref_gmms, g.nghbr_gmms, g.R, g.t,
+                               inp.is_valid, cam_dev, inp.thres)
 
         with torch.no_grad():
             ref_out = ref_call()
@@ -518,8 +536,8 @@ def main():
         ms_ref = r0.elapsed_time(r1) / 3
         reference_cuda = {"ms_per_cost_volume": ms_ref, "frames_per_s_cost_only": B * 1e3 / (N_ITER * ms_ref),
                           "ours_ms_per_cost_volume_drop_in": o0.elapsed_time(o1) / 10,
-                          "frac_elements_beyond_1e-4": frac_diff,
-                          "note": "est_costvolume_CW operator sequence of the reference on CUDA tensors (stock ATen "
+                          "frac_elements_beyond_1e-4": frac_diff, "kind": ref_kind,
+                          "note": "est_costvolume_CW of the reference on CUDA tensors (stock ATen "
                                   "grid_sample / repeat / elementwise kernels), same B=%d batch; frames/s counts %d such "
                                   "calls per frame and nothing else" % (B, N_ITER)}
         del ref_out, ours_out
@@ -528,7 +546,7 @@ def main():
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         fps, info = cpu_reference_frames(args.config, steps=8, warmup=1, budget_s=20.0)
-        cpu_baseline = {"value": fps, "unit": "frames/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]}
+        cpu_baseline = {"value": fps, "unit": "frames/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
     line = {
         "metric": METRIC, "value": frames_per_s, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

@@ -38,6 +38,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--hypotheses", type=int, default=64)
     ap.add_argument("--views", type=int, default=4)
+    ap.add_argument("--unfused-loss", action="store_true",
+                    help="materialise the N_iter upsampled (B,2,4H,4W) predictions and evaluate the NLL in torch (the "
+                         "reference's data flow) instead of the fused upsample+NLL kernels (SURVEY §8 f-2)")
     args = ap.parse_args()
     rank, local_rank, world = md.env_world()
     torch.cuda.set_device(local_rank)
@@ -64,9 +67,14 @@ def main():
     for step in range(args.steps + 2):
         if step == 2:
             torch.cuda.synchronize(); md.barrier(); t0 = time.perf_counter()
-        preds = head(inp.ref_feat, inp.nghbr_feat, inp.ref_gmms, inp.nghbr_gmms, x_d3, inp.nghbr_poses,
-                     inp.is_valid, inp.cam_intrins)
-        loss = gaussian_nll(preds, gt, mask)
+        if args.unfused_loss:
+            preds = head(inp.ref_feat, inp.nghbr_feat, inp.ref_gmms, inp.nghbr_gmms, x_d3, inp.nghbr_poses,
+                         inp.is_valid, inp.cam_intrins)
+            loss = gaussian_nll(preds, gt, mask)
+        else:                                                              # f-2: no (B,2,4H,4W) tensors, fwd or bwd
+            preds_q, up_mask = head.forward_quarter(inp.ref_feat, inp.nghbr_feat, inp.ref_gmms, inp.nghbr_gmms, x_d3,
+                                                    inp.nghbr_poses, inp.is_valid, inp.cam_intrins)
+            loss = head.loss(preds_q, up_mask, gt, mask)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         reducer()                                                          # one 3 MB all-reduce
@@ -77,6 +85,7 @@ def main():
     dt = time.perf_counter() - t0
     if rank == 0:
         print(json.dumps({"config": "train head, ScanNet shape", "n_gpus": world, "global_batch": gb, "steps": args.steps,
+                          "loss_path": "unfused (torch NLL on upsampled predictions)" if args.unfused_loss else "fused upsample+NLL kernels",
                           "ms_per_step": 1e3 * dt / args.steps, "frames_per_s": gb * args.steps / dt,
                           "loss_first": losses[0], "loss_last": losses[-1], "trainable_params": reducer.bucket.numel()}))
     md.shutdown()

@@ -186,10 +186,12 @@ int magnet_gaussian_update_bwd_f32(const float* grad_out, const float* d_output,
 int magnet_relative_poses_f32(const float* ext_ref, const float* ext_nghbr, int32_t B, int32_t V, float* poses_out,
                               int32_t* is_valid_out, void* stream);
 /*
- * magnet_camera_rays_f32 replaces get_ray_array + get_cam_intrinsics (data/dataloader_scannet.py:113-153):
- * raw_intrinsics (B,6) float64 on the device = fx, fy, cx, cy of the raw image and its width, height;
- * intM_out (B,3,3) = intrinsics scaled to the H x W grid; rays_out (B,3,H*W) = K_raw^-1 (pixel centre), z = 1.
- * Evaluated in fp64 and rounded once, bit-identical to the numpy original.
+ * magnet_camera_rays_f32 replaces get_ray_array + get_cam_intrinsics (data/dataloader_scannet.py:113-153 and the
+ * crop-margin variant data/dataloader_kitti.py:94-127): raw_intrinsics (B,8) float64 on the device =
+ * fx, fy, cx, cy of the raw image; img_W, img_H = size of the (cropped) image the grid spans; left_margin, top_margin
+ * = crop offsets in raw pixels (ScanNet: the raw size and 0, 0; KITTI: 1216, 352, (raw_W-1216)/2, raw_H-352).
+ * intM_out (B,3,3) = intrinsics of the H x W grid; rays_out (B,3,H*W) = K_raw^-1 (pixel centre), z = 1.
+ * Evaluated in fp64 and rounded once, bit-identical to the numpy originals.
  */
 int magnet_camera_rays_f32(const double* raw_intrinsics, int32_t B, int32_t H, int32_t W, float* intM_out,
                            float* rays_out, void* stream);
@@ -205,6 +207,24 @@ int magnet_convex_upsample_fwd_f32(const float* depth, const float* up_mask, int
 int magnet_convex_upsample_bwd_f32(const float* grad_out, const float* depth, const float* up_mask, int32_t B,
                                    int32_t CH, int32_t H, int32_t W, int32_t k, float* grad_depth, float* grad_mask,
                                    void* stream);
+
+/*
+ * Convex upsampling fused with the Gaussian negative log-likelihood — replaces, per prediction of pred_list,
+ * upsample_depth_via_mask (models/MAGNET.py:15-27,172-173) followed by MagnetLoss's term (utils/losses.py:39-49):
+ *   nll = (mu - gt)^2 / (2 var) + 0.5 log(var),  var = max(sigma^2, 1e-10),  over the pixels where gt_mask != 0.
+ * depth (B,2,H,W) quarter-resolution [mu, sigma]; up_mask (B,9*k*k,H,W); gt (B,1,k*H,k*W); gt_mask (B,1,k*H,k*W)
+ * uint8.  The (B,2,k*H,k*W) prediction is never materialised.
+ * forward: partial[magnet_upsample_nll_partials(B,H,W,k)] receives one partial sum of nll per CTA (the caller adds
+ *   them — deterministic — and divides by the number of supervised pixels).
+ * backward: scale = upstream gradient * gamma^(n-i-1) / number of supervised pixels; grad_depth (B,2,H,W) is
+ *   ACCUMULATED (the caller zeroes it), grad_mask (B,9*k*k,H,W) is written.
+ */
+int magnet_upsample_nll_partials(int32_t B, int32_t H, int32_t W, int32_t k);
+int magnet_upsample_nll_fwd_f32(const float* depth, const float* up_mask, const float* gt, const uint8_t* gt_mask,
+                                int32_t B, int32_t H, int32_t W, int32_t k, float* partial, void* stream);
+int magnet_upsample_nll_bwd_f32(const float* depth, const float* up_mask, const float* gt, const uint8_t* gt_mask,
+                                float scale, int32_t B, int32_t H, int32_t W, int32_t k, float* grad_depth,
+                                float* grad_mask, void* stream);
 
 #ifdef __cplusplus
 }

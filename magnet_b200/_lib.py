@@ -30,6 +30,7 @@ EXPORTS = (
     "magnet_repack_tiled32_f32", "magnet_repack_pixc_f32", "magnet_sample_depths_f32", "magnet_gaussian_update_fwd_f32",
     "magnet_gaussian_update_bwd_f32", "magnet_convex_upsample_fwd_f32", "magnet_convex_upsample_bwd_f32",
     "magnet_relative_poses_f32", "magnet_camera_rays_f32",
+    "magnet_upsample_nll_partials", "magnet_upsample_nll_fwd_f32", "magnet_upsample_nll_bwd_f32",
 )
 
 
@@ -107,6 +108,14 @@ def lib() -> C.CDLL:
     L.magnet_relative_poses_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.magnet_camera_rays_f32.restype = C.c_int
     L.magnet_camera_rays_f32.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.magnet_upsample_nll_partials.restype = C.c_int
+    L.magnet_upsample_nll_partials.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    L.magnet_upsample_nll_fwd_f32.restype = C.c_int
+    L.magnet_upsample_nll_fwd_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                              C.c_int32, C.c_void_p, C.c_void_p]
+    L.magnet_upsample_nll_bwd_f32.restype = C.c_int
+    L.magnet_upsample_nll_bwd_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32,
+                                              C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     if L.magnet_abi_version() != MAGNET_ABI_VERSION:
         raise MagnetError(f"ABI version mismatch: library {L.magnet_abi_version()} != binding {MAGNET_ABI_VERSION}")
     _lib = L

@@ -35,6 +35,10 @@ cudaError_t launch_upsample_fwd(const float* depth, const float* mask, int B, in
 cudaError_t launch_upsample_bwd(const float* gout, const float* depth, const float* mask, int B, int CH, int H, int W,
                                 int k, float* gdepth, float* gmask, cudaStream_t st);
 cudaError_t launch_cost_f_bwd(const BwdParams& p, cudaStream_t st, int* launches);
+cudaError_t launch_upsample_nll_fwd(const float* depth, const float* mask, const float* gt, const uint8_t* gtm, int B,
+                                    int H, int W, int k, float* partial, cudaStream_t st);
+cudaError_t launch_upsample_nll_bwd(const float* depth, const float* mask, const float* gt, const uint8_t* gtm, float scale,
+                                    int B, int H, int W, int k, float* gdepth, float* gmask, cudaStream_t st);
 }  // namespace magnet
 
 namespace {
@@ -295,6 +299,33 @@ int magnet_convex_upsample_bwd_f32(const float* grad_out, const float* depth, co
   if (CH != 1 && CH != 2) return MAGNET_ERR_UNSUPPORTED;
   cudaError_t e = magnet::launch_upsample_bwd(grad_out, depth, up_mask, B, CH, H, W, k, grad_depth, grad_mask,
                                               (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e);
+  g_launches += 1;
+  return MAGNET_OK;
+}
+
+int magnet_upsample_nll_partials(int32_t B, int32_t H, int32_t W, int32_t k) {
+  if (B <= 0 || H <= 0 || W <= 0 || k <= 0) return MAGNET_ERR_SHAPE;
+  return B * H * k * ((W * k + 127) / 128);
+}
+
+int magnet_upsample_nll_fwd_f32(const float* depth, const float* up_mask, const float* gt, const uint8_t* gt_mask,
+                                int32_t B, int32_t H, int32_t W, int32_t k, float* partial, void* stream) {
+  if (!depth || !up_mask || !gt || !gt_mask || !partial) return MAGNET_ERR_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || k <= 0 || B > 65535 || H * k > 65535) return MAGNET_ERR_SHAPE;
+  cudaError_t e = magnet::launch_upsample_nll_fwd(depth, up_mask, gt, gt_mask, B, H, W, k, partial, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e);
+  g_launches += 1;
+  return MAGNET_OK;
+}
+
+int magnet_upsample_nll_bwd_f32(const float* depth, const float* up_mask, const float* gt, const uint8_t* gt_mask,
+                                float scale, int32_t B, int32_t H, int32_t W, int32_t k, float* grad_depth,
+                                float* grad_mask, void* stream) {
+  if (!depth || !up_mask || !gt || !gt_mask || !grad_depth || !grad_mask) return MAGNET_ERR_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || k <= 0 || B > 65535 || H * k > 65535) return MAGNET_ERR_SHAPE;
+  cudaError_t e = magnet::launch_upsample_nll_bwd(depth, up_mask, gt, gt_mask, scale, B, H, W, k, grad_depth, grad_mask,
+                                                  (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e);
   g_launches += 1;
   return MAGNET_OK;

@@ -217,31 +217,143 @@ __global__ void relative_poses_kernel(const float* __restrict__ ext_ref, const f
   for (int e = 0; e < 16; ++e) poses[(size_t)idx * 16 + e] = ok ? out[e] : 0.0f;
 }
 
-// data/dataloader_scannet.py:113-153 (get_ray_array + get_cam_intrinsics): quarter-resolution intrinsics and the
-// per-pixel rays K_raw^-1 (x+0.5, y+0.5, 1) scaled to the raw image — evaluated in fp64 like the numpy original and
-// rounded to fp32 once, so the result is bit-identical to the reference's arrays.
-// raw (B,6) doubles: fx, fy, cx, cy (raw image), raw_W, raw_H.
+// data/dataloader_scannet.py:113-153 and data/dataloader_kitti.py:94-127 (get_ray_array + get_cam_intrinsics):
+// grid-resolution intrinsics and the per-pixel rays K_raw^-1 (pixel centre) — evaluated in fp64 like the numpy originals
+// and rounded to fp32 once, so the result is bit-identical to the reference's arrays.
+// raw (B,8) doubles: fx, fy, cx, cy of the raw image; img_W, img_H = size of the (cropped) image the H x W grid spans;
+// left_margin, top_margin = crop offsets (KITTI: raw_W-1216 over 2, raw_H-352; ScanNet: img = raw image, margins 0).
+//   intM:  fx*(W/img_W), fy*(H/img_H), (cx-left)*(W/img_W), (cy-top)*(H/img_H)
+//   ray_x: (((x+0.5)*(img_W/W) - cx) + left) / fx      (with left == 0 the "+ left" is exact: ScanNet's formula)
 __global__ void camera_rays_kernel(const double* __restrict__ raw, int H, int W, float* __restrict__ intM,
                                    float* __restrict__ rays) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const size_t b = blockIdx.y;
-  const double fx = raw[b * 6 + 0], fy = raw[b * 6 + 1], cx = raw[b * 6 + 2], cy = raw[b * 6 + 3];
-  const double rw = raw[b * 6 + 4], rh = raw[b * 6 + 5];
+  const double fx = raw[b * 8 + 0], fy = raw[b * 8 + 1], cx = raw[b * 8 + 2], cy = raw[b * 8 + 3];
+  const double iw = raw[b * 8 + 4], ih = raw[b * 8 + 5], left = raw[b * 8 + 6], top = raw[b * 8 + 7];
   if (n == 0) {
     float* K = intM + b * 9;
     for (int e = 0; e < 9; ++e) K[e] = 0.0f;
-    K[0] = (float)(fx * ((double)W / rw));
-    K[4] = (float)(fy * ((double)H / rh));
-    K[2] = (float)(cx * ((double)W / rw));
-    K[5] = (float)(cy * ((double)H / rh));
+    K[0] = (float)(fx * ((double)W / iw));
+    K[4] = (float)(fy * ((double)H / ih));
+    K[2] = (float)((cx - left) * ((double)W / iw));
+    K[5] = (float)((cy - top) * ((double)H / ih));
     K[8] = 1.0f;
   }
   if (n >= H * W) return;
   const int x = n % W, y = n / W;
   const size_t HW = (size_t)H * W;
-  rays[(b * 3 + 0) * HW + n] = (float)((((double)x + 0.5) * (rw / (double)W) - cx) / fx);
-  rays[(b * 3 + 1) * HW + n] = (float)((((double)y + 0.5) * (rh / (double)H) - cy) / fy);
+  rays[(b * 3 + 0) * HW + n] = (float)((((((double)x + 0.5) * (iw / (double)W)) - cx) + left) / fx);
+  rays[(b * 3 + 1) * HW + n] = (float)((((((double)y + 0.5) * (ih / (double)H)) - cy) + top) / fy);
   rays[(b * 3 + 2) * HW + n] = 1.0f;
+}
+
+// ---- convex upsampling fused with the Gaussian NLL (utils/losses.py:34-50) ---------------------------
+// One thread per full-resolution pixel: softmax over the 9 mask logits, the upsampled (mu, sigma) of
+// upsample_depth_via_mask (MAGNET.py:15-27) and, where gt_mask is set, nll = (mu-gt)^2 / (2 var) + 0.5 log(var),
+// var = max(sigma^2, 1e-10).  The (B,2,kH,kW) prediction is never written: forward emits one partial sum per CTA
+// (summed by the caller: deterministic), backward scatters straight into grad_depth / grad_mask.
+__device__ __forceinline__ void upsampled_gaussian(const float* __restrict__ depth, const float* __restrict__ mask,
+                                                   size_t b, int H, int W, int k, int x, int y, int kx, int ky,
+                                                   float (&w)[9], float& mu, float& sg) {
+  const size_t HW = (size_t)H * W;
+  const float* mp = mask + (b * 9 * k * k + (size_t)ky * k + kx) * HW + (size_t)y * W + x;
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { w[i] = mp[(size_t)i * k * k * HW]; m = fmaxf(m, w[i]); }
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { w[i] = expf(w[i] - m); s += w[i]; }
+  const float inv = 1.0f / s;
+  mu = sg = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    w[i] *= inv;
+    const int yy = y + i / 3 - 1, xx = x + i % 3 - 1;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      mu = __fmaf_rn(w[i], depth[(b * 2 + 0) * HW + (size_t)yy * W + xx], mu);
+      sg = __fmaf_rn(w[i], depth[(b * 2 + 1) * HW + (size_t)yy * W + xx], sg);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) upsample_nll_fwd_kernel(const float* __restrict__ depth, const float* __restrict__ mask,
+                                                                const float* __restrict__ gt, const uint8_t* __restrict__ gtm,
+                                                                int H, int W, int k, float* __restrict__ partial) {
+  const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y;
+  const size_t b = blockIdx.z;
+  float nll = 0.0f;
+  if (X < W * k) {
+    const size_t o = (b * H * k + Y) * (size_t)(W * k) + X;
+    if (gtm[o]) {
+      float w[9], mu, sg;
+      upsampled_gaussian(depth, mask, b, H, W, k, X / k, Y / k, X % k, Y % k, w, mu, sg);
+      const float var = fmaxf(sg * sg, 1e-10f), d = mu - gt[o];
+      nll = (d * d) / (2.0f * var) + 0.5f * logf(var);
+    }
+  }
+  __shared__ float red[4];
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) nll += __shfl_xor_sync(0xffffffffu, nll, s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = nll;
+  __syncthreads();
+  if (threadIdx.x == 0)
+    partial[(b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+}
+
+// scale = upstream gradient * iteration weight / number of supervised pixels
+__global__ void __launch_bounds__(128) upsample_nll_bwd_kernel(const float* __restrict__ depth, const float* __restrict__ mask,
+                                                                const float* __restrict__ gt, const uint8_t* __restrict__ gtm,
+                                                                float scale, int H, int W, int k, float* __restrict__ gdepth,
+                                                                float* __restrict__ gmask) {
+  const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y;
+  const size_t b = blockIdx.z;
+  if (X >= W * k) return;
+  const int x = X / k, kx = X % k, y = Y / k, ky = Y % k;
+  const size_t HW = (size_t)H * W;
+  const size_t moff = (b * 9 * k * k + (size_t)ky * k + kx) * HW + (size_t)y * W + x;
+  const size_t o = (b * H * k + Y) * (size_t)(W * k) + X;
+  if (!gtm[o]) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) gmask[moff + (size_t)i * k * k * HW] = 0.0f;
+    return;
+  }
+  float w[9], mu, sg;
+  upsampled_gaussian(depth, mask, b, H, W, k, x, y, kx, ky, w, mu, sg);
+  const float var = fmaxf(sg * sg, 1e-10f), d = mu - gt[o];
+  const float g_mu = scale * d / var;
+  // var[var < 1e-10] = 1e-10 (losses.py:45) cuts the gradient to sigma where it clamps
+  const float g_sg = (sg * sg < 1e-10f) ? 0.0f : scale * (1.0f / sg - (d * d) / (var * sg));
+  float t[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    t[i] = 0.0f;
+    const int yy = y + i / 3 - 1, xx = x + i % 3 - 1;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      const size_t q = (size_t)yy * W + xx;
+      t[i] = __fmaf_rn(g_sg, depth[(b * 2 + 1) * HW + q], g_mu * depth[(b * 2 + 0) * HW + q]);
+      atomicAdd(gdepth + (b * 2 + 0) * HW + q, g_mu * w[i]);
+      atomicAdd(gdepth + (b * 2 + 1) * HW + q, g_sg * w[i]);
+    }
+  }
+  float dot = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) dot = __fmaf_rn(w[i], t[i], dot);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) gmask[moff + (size_t)i * k * k * HW] = w[i] * (t[i] - dot);
+}
+
+cudaError_t launch_upsample_nll_fwd(const float* depth, const float* mask, const float* gt, const uint8_t* gtm, int B,
+                                    int H, int W, int k, float* partial, cudaStream_t st) {
+  dim3 grid((W * k + 127) / 128, H * k, B);
+  upsample_nll_fwd_kernel<<<grid, 128, 0, st>>>(depth, mask, gt, gtm, H, W, k, partial);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_upsample_nll_bwd(const float* depth, const float* mask, const float* gt, const uint8_t* gtm, float scale,
+                                    int B, int H, int W, int k, float* gdepth, float* gmask, cudaStream_t st) {
+  dim3 grid((W * k + 127) / 128, H * k, B);
+  upsample_nll_bwd_kernel<<<grid, 128, 0, st>>>(depth, mask, gt, gtm, scale, H, W, k, gdepth, gmask);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_relative_poses(const float* ext_ref, const float* ext_nghbr, int B, int V, float* poses,

@@ -150,10 +150,20 @@ class MagnetHead(nn.Module):
         return ops.convex_upsample(depth, up_mask, k)
 
     def forward(self, ref_feat, nghbr_feat, ref_gmms, nghbr_gmms, x_d3, nghbr_poses, is_valid, cam_intrins):
+        preds, mask = self.forward_quarter(ref_feat, nghbr_feat, ref_gmms, nghbr_gmms, x_d3, nghbr_poses, is_valid,
+                                           cam_intrins)
+        return [self.upsample(pr, mask, self.downsample_ratio) for pr in preds]
+
+    def forward_quarter(self, ref_feat, nghbr_feat, ref_gmms, nghbr_gmms, x_d3, nghbr_poses, is_valid, cam_intrins):
+        """The N_iter quarter-resolution predictions and the upsampling mask, NOT upsampled: what the fused
+        upsample + NLL loss (``loss`` below) consumes during training."""
         plan = MatchingPlan(ref_feat, nghbr_feat, nghbr_gmms, nghbr_poses, is_valid, cam_intrins, thres=self.thres)
         preds = matching_loop(plan, ref_gmms, x_d3, self.g_net, self.n_iter, self.k_list)
-        mask = self.mask_head(x_d3)
-        return [self.upsample(pr, mask, self.downsample_ratio) for pr in preds[1:]]
+        return preds[1:], self.mask_head(x_d3)
+
+    def loss(self, preds_quarter, mask, gt_depth, gt_depth_mask, gamma: float = 0.8):
+        """MagnetLoss 'gaussian' (utils/losses.py:34-50) of the upsampled predictions without materialising them."""
+        return ops.magnet_loss(preds_quarter, mask, gt_depth, gt_depth_mask, self.downsample_ratio, gamma)
 
 
 class MAGNET(nn.Module):

@@ -317,6 +317,62 @@ def convex_upsample(depth: torch.Tensor, up_mask: torch.Tensor, k: int) -> torch
     return ConvexUpsample.apply(depth, up_mask, k)
 
 
+class UpsampleNLL(torch.autograd.Function):
+    """mean over the supervised pixels of the Gaussian NLL of ONE convex-upsampled prediction — upsample_depth_via_mask
+    (MAGNET.py:15-27) + the per-prediction term of MagnetLoss (utils/losses.py:39-49) in one kernel each way; the
+    (B,2,kH,kW) prediction never reaches HBM.  Differentiable in depth (B,2,H,W) and up_mask (B,9k^2,H,W)."""
+
+    @staticmethod
+    def forward(ctx, depth, up_mask, gt, gt_mask_u8, k, count):
+        depth = _need_cuda_f32("depth", depth)
+        up_mask = _need_cuda_f32("up_mask", up_mask)
+        gt = _need_cuda_f32("gt", gt)
+        B, CH, H, W = depth.shape
+        if CH != 2:
+            raise _lib.MagnetError(f"depth must be (B,2,H,W) [mu, sigma], got {tuple(depth.shape)}")
+        _expect("up_mask", up_mask, (B, 9 * k * k, H, W))
+        _expect("gt", gt, (B, 1, k * H, k * W))
+        if gt_mask_u8.dtype != torch.uint8 or not gt_mask_u8.is_cuda or tuple(gt_mask_u8.shape) != (B, 1, k * H, k * W):
+            raise _lib.MagnetError("gt_mask must be a CUDA uint8 tensor of shape (B,1,k*H,k*W)")
+        gt_mask_u8 = gt_mask_u8.contiguous()
+        dev = _same_device(("depth", depth), ("up_mask", up_mask), ("gt", gt), ("gt_mask", gt_mask_u8))
+        partial = torch.empty(lib().magnet_upsample_nll_partials(B, H, W, k), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            check(lib().magnet_upsample_nll_fwd_f32(depth.data_ptr(), up_mask.data_ptr(), gt.data_ptr(), gt_mask_u8.data_ptr(),
+                                                    B, H, W, k, partial.data_ptr(), _stream(dev)), "magnet_upsample_nll_fwd_f32")
+        ctx.save_for_backward(depth, up_mask, gt, gt_mask_u8)
+        ctx.k, ctx.count = k, float(count)
+        return partial.sum(dtype=torch.float64).to(torch.float32) / ctx.count
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        depth, up_mask, gt, gtm = ctx.saved_tensors
+        B, _, H, W = depth.shape
+        g_depth = torch.zeros_like(depth)
+        g_mask = torch.empty_like(up_mask)
+        scale = float(grad_out) / ctx.count
+        with torch.cuda.device(depth.device):
+            check(lib().magnet_upsample_nll_bwd_f32(depth.data_ptr(), up_mask.data_ptr(), gt.data_ptr(), gtm.data_ptr(), scale,
+                                                    B, H, W, ctx.k, g_depth.data_ptr(), g_mask.data_ptr(),
+                                                    _stream(depth.device)), "magnet_upsample_nll_bwd_f32")
+        return g_depth, g_mask, None, None, None, None
+
+
+def magnet_loss(pred_list, up_mask, gt, gt_mask, k: int, gamma: float = 0.8):
+    """MagnetLoss 'gaussian' (utils/losses.py:34-50) on the QUARTER-RESOLUTION predictions of the matching loop and the
+    shared upsampling mask: sum_i gamma^(n-i-1) * mean NLL(upsample(pred_i)), each term one fused kernel (f-2).
+    pred_list: the (B,2,H,W) Gaussians pred_1..pred_n; gt (B,1,kH,kW); gt_mask bool / uint8 of the same shape."""
+    gtm = gt_mask.to(torch.uint8)
+    count = int(gtm.sum().item())          # one host read per step; the reference's boolean indexing syncs 3x per term
+    if count == 0:
+        raise _lib.MagnetError("gt_mask selects no pixel")
+    n = len(pred_list)
+    loss = 0.0
+    for i, pred in enumerate(pred_list):
+        loss = loss + gamma ** (n - i - 1) * UpsampleNLL.apply(pred, up_mask, gt, gtm, k, count)
+    return loss
+
+
 def relative_poses(ext_ref: torch.Tensor, ext_nghbr: torch.Tensor):
     """data_preprocess (utils/utils.py:72-98) on the device: ext_ref (B,4,4), ext_nghbr (V,B,4,4) ->
     (nghbr_poses (B,V,4,4), is_valid (B,V) int32)."""
@@ -333,10 +389,15 @@ def relative_poses(ext_ref: torch.Tensor, ext_nghbr: torch.Tensor):
 
 
 def camera_rays(raw_intrinsics: torch.Tensor, H: int, W: int):
-    """get_cam_intrinsics (data/dataloader_scannet.py:113-153) on the device: raw_intrinsics (B,6) float64
-    [fx, fy, cx, cy, raw_W, raw_H] -> cam_intrins dict {'intM' (B,3,3), 'unit_ray_array_2D' (B,3,H*W)} (device)."""
-    if not raw_intrinsics.is_cuda or raw_intrinsics.dtype != torch.float64:
-        raise _lib.MagnetError("raw_intrinsics must be a CUDA float64 tensor (B,6)")
+    """get_cam_intrinsics (data/dataloader_scannet.py:113-153, data/dataloader_kitti.py:94-127) on the device:
+    raw_intrinsics (B,8) float64 [fx, fy, cx, cy, img_W, img_H, left_margin, top_margin] (a (B,6) tensor
+    [fx, fy, cx, cy, raw_W, raw_H] is accepted as the ScanNet case: no crop) -> cam_intrins dict
+    {'intM' (B,3,3), 'unit_ray_array_2D' (B,3,H*W)} (device)."""
+    if not raw_intrinsics.is_cuda or raw_intrinsics.dtype != torch.float64 or raw_intrinsics.dim() != 2 \
+            or raw_intrinsics.shape[1] not in (6, 8):
+        raise _lib.MagnetError("raw_intrinsics must be a CUDA float64 tensor (B,8) (or (B,6) without crop margins)")
+    if raw_intrinsics.shape[1] == 6:
+        raw_intrinsics = torch.cat([raw_intrinsics, torch.zeros_like(raw_intrinsics[:, :2])], dim=1)
     raw_intrinsics = raw_intrinsics.contiguous()
     B = raw_intrinsics.shape[0]
     intM = torch.empty(B, 3, 3, device=raw_intrinsics.device, dtype=torch.float32)

@@ -288,23 +288,47 @@ def relative_poses(ext_ref, ext_nghbr):
 
 
 def camera_rays(raw, H, W):
-    """get_ray_array + get_cam_intrinsics (data/dataloader_scannet.py:113-153): raw (B,6) float64 = fx, fy, cx, cy
-    of the raw image, raw_W, raw_H -> intM (B,3,3) fp32 scaled to the H x W grid, rays (B,3,H*W) fp32 through the
-    pixel centres (x+0.5, y+0.5); everything in fp64 until the final cast, as in the numpy original."""
+    """get_ray_array + get_cam_intrinsics (data/dataloader_scannet.py:113-153; crop-margin variant
+    data/dataloader_kitti.py:94-127): raw (B,8) float64 = fx, fy, cx, cy of the raw image, img_W, img_H (the cropped image
+    the grid spans), left_margin, top_margin ((B,6) = no crop: ScanNet) -> intM (B,3,3) fp32 of the H x W grid, rays
+    (B,3,H*W) fp32 through the pixel centres (x+0.5, y+0.5); everything in fp64 until the final cast, operation by
+    operation as in the numpy originals (with zero margins the KITTI expressions reduce exactly to the ScanNet ones)."""
     raw = np.asarray(raw, dtype=np.float64)
+    if raw.shape[1] == 6:
+        raw = np.concatenate([raw, np.zeros((raw.shape[0], 2))], axis=1)
     B = raw.shape[0]
     intM = np.zeros((B, 3, 3), dtype=np.float64)
     rays = np.ones((B, H, W, 3), dtype=np.float64)
     xs = np.arange(W, dtype=np.float64) + 0.5
     ys = np.arange(H, dtype=np.float64) + 0.5
     for b in range(B):
-        fx, fy, cx, cy, rw, rh = raw[b]
+        fx, fy, cx, cy, iw, ih, left, top = raw[b]
         intM[b, 2, 2] = 1.0
-        intM[b, 0, 0] = fx * (W / rw)
-        intM[b, 1, 1] = fy * (H / rh)
-        intM[b, 0, 2] = cx * (W / rw)
-        intM[b, 1, 2] = cy * (H / rh)
-        rays[b, :, :, 0] = ((xs * (rw / W)) - cx)[None, :] / fx
-        rays[b, :, :, 1] = ((ys * (rh / H)) - cy)[:, None] / fy
+        intM[b, 0, 0] = fx * (W / iw)
+        intM[b, 1, 1] = fy * (H / ih)
+        intM[b, 0, 2] = (cx - left) * (W / iw)
+        intM[b, 1, 2] = (cy - top) * (H / ih)
+        rays[b, :, :, 0] = (((xs * (iw / W)) - cx) + left)[None, :] / fx
+        rays[b, :, :, 1] = (((ys * (ih / H)) - cy) + top)[:, None] / fy
     rays2d = np.reshape(np.transpose(rays, (0, 3, 1, 2)), (B, 3, H * W))
     return intM.astype(np.float32), rays2d.astype(np.float32)
+
+
+def gaussian_nll(pred_list, gt, mask, gamma=0.8):
+    """MagnetLoss 'gaussian' (utils/losses.py:34-50): sum_i gamma^(n-i-1) mean_{mask}[(mu-gt)^2 / (2 var) + 0.5 log var],
+    var = max(sigma^2, 1e-10).  pred_list: (B,2,H,W) arrays at the resolution of gt (B,1,H,W); mask bool (B,1,H,W).
+    fp32 operations in the reference's order."""
+    gt = np.asarray(gt, dtype=np.float32)
+    mask = np.asarray(mask, dtype=bool)
+    g = gt[mask]
+    n = len(pred_list)
+    loss = np.float32(0.0)
+    for i, pred in enumerate(pred_list):
+        pred = np.asarray(pred, dtype=np.float32)
+        mu, sigma = pred[:, 0:1][mask], pred[:, 1:2][mask]
+        var = np.square(sigma)
+        var[var < 1e-10] = 1e-10
+        nll = (np.square(mu - g) / (np.float32(2) * var)) + (np.float32(0.5) * np.log(var))
+        loss = np.float32(loss + np.float32(gamma ** (n - i - 1)) * np.mean(nll, dtype=np.float32))
+    return loss
+

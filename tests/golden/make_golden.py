@@ -107,6 +107,116 @@ def main():
                         grad_out=gout.numpy(), grad_d_output=d_output.grad.numpy(),
                         depth=depth.numpy(), mask=mask.numpy(), up=up.numpy(), **ks)
     print("update / upsample / k_list written")
+    camera_prep_and_loss(g)
+
+
+def _camera_prep_case():
+    """(V+1) x B extrinsics with a NaN source pose and a NaN reference pose (same generator as the tests use)."""
+    rng = np.random.default_rng(9)
+    B, V = 3, 4
+    ext = np.tile(np.eye(4, dtype=np.float32), (V + 1, B, 1, 1))
+    for f in range(V + 1):
+        for b in range(B):
+            a = rng.uniform(-0.2, 0.2, 3)
+            Rz = np.array([[np.cos(a[0]), -np.sin(a[0]), 0], [np.sin(a[0]), np.cos(a[0]), 0], [0, 0, 1]])
+            Ry = np.array([[np.cos(a[1]), 0, np.sin(a[1])], [0, 1, 0], [-np.sin(a[1]), 0, np.cos(a[1])]])
+            ext[f, b, :3, :3] = (Rz @ Ry).astype(np.float32)
+            ext[f, b, :3, 3] = rng.uniform(-1, 1, 3).astype(np.float32)
+    ext_ref, ext_nghbr = ext[V // 2].copy(), np.delete(ext, V // 2, axis=0).copy()
+    ext_nghbr[0, 1, 0, 0] = np.nan          # NaN source extrinsic: that view is invalid
+    ext_ref[2, 1, 1] = np.nan               # NaN reference extrinsic: all views of that element invalid
+    return ext_ref, ext_nghbr
+
+
+SCANNET_RAW = [1169.621094, 1167.105103, 646.295044, 489.927032, 1296.0, 968.0]      # fx fy cx cy raw_W raw_H
+KITTI_RAW = [721.5377, 721.5377, 609.5593, 172.854, 1242.0, 375.0]                    # K_cam2 of a 1242 x 375 drive
+
+
+def camera_prep_and_loss(g):
+    """SURVEY §8 f-4 / f-2 pins: the reference's own data_preprocess (utils/utils.py:72-98), get_cam_intrinsics of the
+    ScanNet and KITTI loaders (data/dataloader_scannet.py:113-153, data/dataloader_kitti.py:94-127) and MagnetLoss
+    (utils/losses.py:34-50, with autograd gradients through upsample_depth_via_mask)."""
+    import tempfile
+    import utils.utils as ref_utils
+    import utils.losses as ref_losses
+    from models.MAGNET import upsample_depth_via_mask
+    # numpy 2 cannot take a torch tensor in np.linalg.inv(tensor) the way the 2021 code does (utils.py:92): hand the
+    # same values over as an ndarray.  Nothing else of data_preprocess is touched.
+    real_inv = np.linalg.inv
+
+    class _NP:
+        def __getattr__(self, name):
+            return getattr(np, name)
+
+    class _LA:
+        def __getattr__(self, name):
+            return getattr(np.linalg, name)
+
+        @staticmethod
+        def inv(a):
+            return real_inv(np.asarray(a))
+
+    shim = _NP()
+    shim.linalg = _LA()
+    ref_utils.np = shim
+    ext_ref, ext_nghbr = _camera_prep_case()
+    V, B = ext_nghbr.shape[:2]
+    frames = [{"extM": torch.from_numpy(ext_nghbr[v])} for v in range(V)]
+    data_array = frames[:V // 2] + [{"extM": torch.from_numpy(ext_ref)}] + frames[V // 2:]
+    _, _, poses, valid = ref_utils.data_preprocess(data_array, B)
+    ref_utils.np = np
+
+    # ScanNet loader: unbound methods on a stub self, intrinsics from a temp 'intrinsic_color.txt'
+    for name in ("pykitti",):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    import data.dataloader_scannet as ds
+    import data.dataloader_kitti as dk
+    H, W = 120, 160
+    stub = types.SimpleNamespace(dpv_H=H, dpv_W=W, raw_WH_dict={"scene0000_00": (int(SCANNET_RAW[4]), int(SCANNET_RAW[5]))})
+    cls = ds.ScannetLoadPreprocess
+    stub.ray_array = cls.get_ray_array(stub)
+    with tempfile.TemporaryDirectory() as td:
+        os.makedirs(os.path.join(td, "intrinsic"))
+        K4 = np.eye(4)
+        K4[0, 0], K4[1, 1], K4[0, 2], K4[1, 2] = SCANNET_RAW[:4]
+        with open(os.path.join(td, "intrinsic", "intrinsic_color.txt"), "w") as f:
+            for row in K4:
+                f.write(" ".join(repr(float(x)) for x in row) + "\n")
+        cam_s = cls.get_cam_intrinsics(stub, td, "scene0000_00")
+    # KITTI loader: crop to 1216 x 352 (left margin (raw_W-1216)/2, top margin raw_H-352)
+    clsk = dk.KittiLoadPreprocess
+    Hk, Wk = 88, 304
+    stubk = types.SimpleNamespace(dpv_H=Hk, dpv_W=Wk, img_H=352, img_W=1216)
+    stubk.ray_array = clsk.get_ray_array(stubk)
+    Kk = np.eye(3)
+    Kk[0, 0], Kk[1, 1], Kk[0, 2], Kk[1, 2] = KITTI_RAW[:4]
+    p_data = types.SimpleNamespace(get_cam2=lambda i: types.SimpleNamespace(size=(int(KITTI_RAW[4]), int(KITTI_RAW[5]))),
+                                   calib=types.SimpleNamespace(K_cam2=Kk))
+    cam_k = clsk.get_cam_intrinsics(stubk, p_data)
+
+    # MagnetLoss on two upsampled predictions, gradients w.r.t. the quarter-resolution predictions and the mask logits
+    preds = [(torch.cat([torch.rand(2, 1, 6, 7, generator=g) * 3 + 0.5, torch.rand(2, 1, 6, 7, generator=g) * 0.4 + 0.05], 1)
+              ).requires_grad_(True) for _ in range(2)]
+    with torch.no_grad():
+        preds[1][0, 1, 2, 3] = 1e-7                       # var below the 1e-10 clamp (losses.py:45)
+    mask = torch.randn(2, 9 * 16, 6, 7, generator=g).requires_grad_(True)
+    gt = torch.rand(2, 1, 24, 28, generator=g) * 3 + 0.4
+    gt_mask = torch.rand(2, 1, 24, 28, generator=g) > 0.3
+    loss_fn = ref_losses.MagnetLoss(types.SimpleNamespace(loss_fn="gaussian", loss_gamma=0.8))
+    ups = [upsample_depth_via_mask(p, mask, 4) for p in preds]
+    loss = loss_fn(ups, gt, gt_mask)
+    loss.backward()
+    np.savez_compressed(os.path.join(HERE, "camera_prep_loss.npz"),
+                        ext_ref=ext_ref, ext_nghbr=ext_nghbr, poses=poses.numpy(), valid=valid.numpy(),
+                        scannet_raw=np.asarray(SCANNET_RAW), scannet_intM=cam_s["intM"].numpy(),
+                        scannet_rays=cam_s["unit_ray_array_2D"].numpy(),
+                        kitti_raw=np.asarray(KITTI_RAW), kitti_intM=cam_k["intM"].numpy(),
+                        kitti_rays=cam_k["unit_ray_array_2D"].numpy(),
+                        pred0=preds[0].detach().numpy(), pred1=preds[1].detach().numpy(), up_mask=mask.detach().numpy(),
+                        gt=gt.numpy(), gt_mask=gt_mask.numpy(), loss=np.float32(loss.item()),
+                        g_pred0=preds[0].grad.numpy(), g_pred1=preds[1].grad.numpy(), g_mask=mask.grad.numpy())
+    print("camera prep + loss written: valid", valid.tolist(), "loss", float(loss))
 
 
 if __name__ == "__main__":

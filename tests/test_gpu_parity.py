@@ -322,15 +322,23 @@ def test_head_training_step_decreases_loss(cuda):
     assert losses[-1] < losses[0]
 
 
-@pytest.mark.parametrize("seed,shape", [(61, dict(B=2, V=2, D=8, H=20, W=28, C=16)), (62, dict(B=1, V=3, D=12, H=16, W=40, C=64))])
-def test_f_volume_backward_matches_autograd_of_reference_ops(cuda, seed, shape):
+@pytest.mark.parametrize("seed,shape,nplanes", [(61, dict(B=2, V=2, D=8, H=20, W=28, C=16), 10),
+                                                (62, dict(B=1, V=3, D=12, H=16, W=40, C=64), 10),
+                                                # F-Net training shape (train_FNet.py:56-66): 80 SID planes, C=64, 120x160
+                                                (63, dict(B=1, V=2, D=8, H=120, W=160, C=64), 80)])
+def test_f_volume_backward_matches_autograd_of_reference_ops(cuda, seed, shape, nplanes):
     """gradients of est_costvolume_F w.r.t. both feature maps against autograd through the ATen port
     of the reference (same operator sequence as homography.py:10-75, run on the same device)."""
     from oracle import torch_ref
     inp = make_inputs(seed=seed, depth="smooth", invalid=[(0, 1)], **shape)
     g = inp.to(cuda)
-    planes = torch.linspace(0.8, 6.0, 10, device=cuda).view(1, -1, 1, 1)
-    gout = torch.randn(shape["B"], 10, shape["H"], shape["W"], device=cuda)
+    if nplanes == 80:                                   # SID plane centres as train_FNet.py builds them
+        idx = np.arange(81)
+        bounds = np.exp(np.log(10.0 + 0.5) * idx / 80) - 0.5
+        planes = torch.from_numpy(((bounds[:-1] + bounds[1:]) / 2).astype(np.float32)).to(cuda).view(1, -1, 1, 1)
+    else:
+        planes = torch.linspace(0.8, 6.0, nplanes, device=cuda).view(1, -1, 1, 1)
+    gout = torch.randn(shape["B"], nplanes, shape["H"], shape["W"], device=cuda)
     r1, s1 = g.ref_feat.clone().requires_grad_(True), g.nghbr_feat.clone().requires_grad_(True)
     ours = magnet_b200.est_costvolume_F(planes, r1, s1, g.R, g.t, inp.is_valid, inp.cam_intrins)
     (ours * gout).sum().backward()
@@ -493,16 +501,45 @@ def test_magnet_module_matches_reference_dataflow(cuda):
 
 
 def test_camera_prep_kernels(cuda):
-    """f-4: on-device relative poses + validity against the numpy restatement of data_preprocess, rays / intrinsics
-    bit-identical to the fp64 numpy restatement of get_cam_intrinsics."""
-    from tests.test_oracle_golden import _camera_prep_case
-    ext_ref, ext_nghbr = _camera_prep_case()
-    want_p, want_v = mo.relative_poses(ext_ref, ext_nghbr)
-    poses, valid = ops.relative_poses(torch.from_numpy(ext_ref).to(cuda), torch.from_numpy(ext_nghbr).to(cuda))
-    assert np.array_equal(valid.cpu().numpy(), want_v)
-    assert np.allclose(poses.cpu().numpy(), want_p, rtol=1e-5, atol=2e-6)
+    """f-4: on-device relative poses + validity and grid intrinsics / rays against the REFERENCE's outputs (golden:
+    utils.data_preprocess, the ScanNet and the KITTI get_cam_intrinsics); rays / intrinsics bit-identical."""
+    from tests.test_oracle_golden import _kitti_raw8
+    z, _ = load_golden("camera_prep_loss")
+    poses, valid = ops.relative_poses(torch.from_numpy(z["ext_ref"]).to(cuda), torch.from_numpy(z["ext_nghbr"]).to(cuda))
+    assert np.array_equal(valid.cpu().numpy(), z["valid"])
+    assert np.allclose(poses.cpu().numpy(), z["poses"], rtol=1e-5, atol=2e-6)
+    cam = ops.camera_rays(torch.from_numpy(z["scannet_raw"][None]).to(cuda), 120, 160)          # (B,6): ScanNet, no crop
+    assert np.array_equal(cam["intM"].cpu().numpy()[0], z["scannet_intM"])
+    assert np.array_equal(cam["unit_ray_array_2D"].cpu().numpy()[0], z["scannet_rays"])
+    cam = ops.camera_rays(torch.from_numpy(_kitti_raw8(z)).to(cuda), 88, 304)                    # KITTI crop margins
+    assert np.array_equal(cam["intM"].cpu().numpy()[0], z["kitti_intM"])
+    assert np.array_equal(cam["unit_ray_array_2D"].cpu().numpy()[0], z["kitti_rays"])
     raw = np.array([[1169.6, 1167.1, 646.3, 489.9, 1296.0, 968.0], [577.9, 578.7, 319.5, 239.5, 640.0, 480.0]])
     cam = ops.camera_rays(torch.from_numpy(raw).to(cuda), 120, 160)
     intM, rays = mo.camera_rays(raw, 120, 160)
     assert np.array_equal(cam["intM"].cpu().numpy(), intM)
     assert np.array_equal(cam["unit_ray_array_2D"].cpu().numpy(), rays)
+
+
+def test_fused_upsample_nll_vs_reference_loss(cuda):
+    """f-2: upsampling + gamma-weighted Gaussian NLL fused (no (B,2,4H,4W) tensors) against the loss and the autograd
+    gradients the REFERENCE produced (MagnetLoss over upsample_depth_via_mask, golden), including a pixel whose variance
+    sits below the 1e-10 clamp."""
+    z, _ = load_golden("camera_prep_loss")
+    p0 = torch.from_numpy(z["pred0"]).to(cuda).requires_grad_(True)
+    p1 = torch.from_numpy(z["pred1"]).to(cuda).requires_grad_(True)
+    mask = torch.from_numpy(z["up_mask"]).to(cuda).requires_grad_(True)
+    gt, gtm = torch.from_numpy(z["gt"]).to(cuda), torch.from_numpy(z["gt_mask"]).to(cuda)
+    loss = ops.magnet_loss([p0, p1], mask, gt, gtm, 4, gamma=0.8)
+    loss.backward()
+    assert abs(float(loss) - float(z["loss"])) <= 2e-5 * abs(float(z["loss"]))
+    for got, want in ((p0.grad, z["g_pred0"]), (p1.grad, z["g_pred1"]), (mask.grad, z["g_mask"])):
+        want = torch.from_numpy(want).to(cuda)
+        assert float((got - want).abs().max()) <= 2e-5 * float(want.abs().max()), float((got - want).abs().max())
+    # and the unfused route of this repo (ConvexUpsample kernels + the NLL in torch) agrees
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("train_head", os.path.join(os.path.dirname(os.path.dirname(__file__)), "examples", "train_head.py"))
+    th = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(th)
+    ups = [ops.convex_upsample(p.detach(), mask.detach(), 4) for p in (p0, p1)]
+    assert abs(float(th.gaussian_nll(ups, gt, gtm)) - float(loss)) <= 2e-5 * abs(float(loss))

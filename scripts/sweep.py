@@ -1,43 +1,79 @@
-"""BASELINE.json configs[4]: stress sweep views x hypotheses at the 640x480 (120x160) grid, one GPU:
-kernel time, algorithmic HBM GB/s and fraction of the measured roofline per point.
-usage: python scripts/sweep.py [out.md]"""
-import json, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch
-import magnet_b200
-from magnet_b200 import ops
-from magnet_b200.synthetic import make_inputs
-from bench import algorithmic_bytes, measured_peak
+"""BASELINE.json configs[4]: stress sweep views x hypotheses at the 640x480 (120x160) grid on 1..8 GPUs (weak scaling:
+every rank owns its own batch of 8, no data-path collective): per point the cost-kernel time (CUDA events, L2 flushed
+between launches, MAX over ranks), algorithmic HBM GB/s and fraction of the measured roofline, for the global-gather
+kernel (fused sampler) and the TMA-staged kernel (fused sampler and drop-in d_volume mode).
 
+    python scripts/sweep.py out.md
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 scripts/sweep.py out.md
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import magnet_b200  # noqa: E402
+from bench import algorithmic_bytes, measured_peak  # noqa: E402
+from magnet_b200 import _lib, dist as md, ops  # noqa: E402
+from magnet_b200.synthetic import make_inputs  # noqa: E402
+
+rank, local_rank, world = md.env_world()
+torch.cuda.set_device(local_rank)
+dev = torch.device("cuda", local_rank)
+md.init_process_group("nccl", device_id=dev)
 peak, src = measured_peak()
+B, H, W, C = 8, 120, 160, 64
+flush = torch.empty(64 * 1024 * 1024, device=dev)
+VS = [int(v) for v in os.environ.get("SWEEP_V", "2,4,8").split(",")]
+DS = [int(d) for d in os.environ.get("SWEEP_D", "32,64,128,256").split(",")]
+
+
+def median_ms(fn, reps=11):
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        md.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(md.max_over_ranks(e0.elapsed_time(e1), device=dev))
+    return sorted(ts)[len(ts) // 2]
+
+
 rows = []
-flush = torch.empty(64 * 1024 * 1024, device="cuda")
-for V in (2, 4, 8):
-    for D in (32, 64, 128, 256):
-        inp = make_inputs(B=8, V=V, D=D, H=120, W=160, C=64, seed=1, depth="smooth")
-        g = inp.to("cuda")
+for V in VS:
+    for D in DS:
+        inp = make_inputs(B=B, V=V, D=D, H=H, W=W, C=C, seed=1 + rank, depth="smooth")
+        g = inp.to(dev)
         plan = magnet_b200.MatchingPlan(g.ref_feat, g.nghbr_feat, g.nghbr_gmms, g.nghbr_poses, inp.is_valid,
                                         inp.cam_intrins, thres=5)
         k = ops.k_array(inp.k.tolist())
-        out = torch.empty(8, D, 120, 160, device="cuda")
-        for _ in range(3):
-            plan.cost(g.ref_gmms, k, out=out)
-        ts = []
-        for _ in range(15):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); plan.cost(g.ref_gmms, k, out=out); e1.record()
-            torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
-        ms = sorted(ts)[len(ts) // 2]
-        ab = algorithmic_bytes(8, V, D, 64, 120 * 160, fused=True)
-        gbs = ab / (ms * 1e-3) / 1e9
-        rows.append((V, D, ms, ab / 1e6, gbs, gbs / peak, 8 / (3 * ms * 1e-3)))
-        print(rows[-1], flush=True)
-        del plan, g, out
+        out = torch.empty(B, D, H, W, device=dev)
+        dvol = ops.sample_depths(g.ref_gmms, k)
+        pix = plan._source(_lib.SRC_PIXC)
+        ms_g = median_ms(lambda: plan.cost(g.ref_gmms, k, out=out, variant=_lib.VARIANT_CELLS))
+        ms_t = median_ms(lambda: plan.cost(g.ref_gmms, k, out=out, variant=_lib.VARIANT_TMA))
+        ms_d = median_ms(lambda: ops.cost_volume(plan.ref_feat, pix, plan.rays, plan.cams, V=V, src_layout=_lib.SRC_PIXC,
+                                                 consistency=True, kappa=5.0, d_volume=dvol, out=out))
+        ab = algorithmic_bytes(B, V, D, C, H * W, fused=True)
+        abd = algorithmic_bytes(B, V, D, C, H * W, fused=False)
+        rows.append((V, D, ab / 1e6, ms_g, ab / ms_g / 1e6 / peak, ms_t, ab / ms_t / 1e6 / peak, ms_d, abd / ms_d / 1e6 / peak,
+                     world * B / (3 * min(ms_g, ms_t) * 1e-3)))
+        if rank == 0:
+            print(rows[-1], flush=True)
+        del plan, g, out, dvol, pix
         torch.cuda.empty_cache()
-md = ["# stress sweep (BASELINE.json configs[4]): fused cost kernel, B=8, 120x160 grid (640x480), C=64, 1x B200",
-      f"peak = {peak:.0f} GB/s ({src}); frames/s = 8 frames / (3 iterations x kernel time), cost kernel only\n",
-      "| views | hypotheses | kernel ms | algorithmic MB | GB/s | frac of HBM roofline | frames/s (kernel only) |", "|---:|---:|---:|---:|---:|---:|---:|"]
-for r in rows:
-    md.append("| %d | %d | %.3f | %.1f | %.0f | %.3f | %.0f |" % r)
-open(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/sweep.md", "w").write("\n".join(md) + "\n")
+if rank == 0:
+    md_lines = [f"# stress sweep (BASELINE.json configs[4]) on {world} x B200: B=8 per GPU, 120x160 grid (640x480), C=64",
+                f"peak = {peak:.0f} GB/s ({src}); kernel ms = median of 11 launches, L2 flushed, max over the {world} ranks; frac = "
+                "algorithmic bytes / kernel time / peak (per GPU); frames/s = all ranks' frames / (3 iterations x best fused kernel)\n",
+                "| views | hyp. | algorithmic MB | gather kernel ms | frac | TMA kernel ms | frac | TMA drop-in ms | frac | frames/s (kernel only) |",
+                "|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|"]
+    for r in rows:
+        md_lines.append("| %d | %d | %.1f | %.3f | %.3f | %.3f | %.3f | %.3f | %.3f | %.0f |" % r)
+    open(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/sweep.md", "w").write("\n".join(md_lines) + "\n")
+md.shutdown()

@@ -346,7 +346,12 @@ def test_f_volume_backward_matches_autograd_of_reference_ops(cuda, seed, shape, 
     cam_d = {k: v.to(cuda) for k, v in inp.cam_intrins.items()}
     theirs = torch_ref.cost_volume_f(planes, r2, s2, g.R, g.t, inp.is_valid, cam_d)
     (theirs * gout).sum().backward()
-    assert float((ours - theirs).abs().max()) <= 1e-4 * float(theirs.abs().max())
+    # the outputs are softmax probabilities: a score error d moves a probability by at most d/2, and fp32 re-association
+    # of the 64-channel sums is worth ~1e-5 of the largest score (peaked volumes at the F-Net shape: |score| ~ 40)
+    with torch.no_grad():
+        smax = float(torch_ref.cost_volume_f(planes, g.ref_feat, g.nghbr_feat, g.R, g.t, inp.is_valid, cam_d,
+                                             apply_softmax=False).abs().max())
+    assert float((ours - theirs).abs().max()) <= max(1e-4 * float(theirs.abs().max()), 1e-5 * smax)
     for a, b, name in ((r1.grad, r2.grad, "ref"), (s1.grad, s2.grad, "src")):
         err = float((a - b).abs().max())
         assert err <= 2e-4 * float(b.abs().max()), (name, err, float(b.abs().max()))

@@ -56,11 +56,12 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(workload):
-    """DRAM bytes per launch of the cost kernel from the committed ncu capture (profiles/), or None."""
+def ncu_traffic(workload, tma=False):
+    """DRAM bytes per launch of the timed cost kernel from the committed ncu --set full capture (profiles/traffic.json:
+    keys "<config>" for the global-gather kernel, "<config>:tma" for the TMA-staged one), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(workload)
+            return json.load(f).get(workload + (":tma" if tma else ""))
     except Exception:
         return None
 
@@ -492,7 +493,7 @@ def main():
     achieved = abytes / (kern_ms * 1e-3) / 1e9
     grid, block, smem = ops.cost_launch_info(B, V, D, C, H, Wd, variant=_lib.VARIANT_CELLS if variant == _lib.VARIANT_CELLS_NOREUSE else variant)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(args.config), "kernel": {_lib.VARIANT_DIRECT: "cost_direct_kernel<CW>", _lib.VARIANT_CELLS: "cost_cells_kernel<64,GAUSS,CW> (TILED32 gather)",
+                "traffic": ncu_traffic(args.config, tma=pixc), "kernel": {_lib.VARIANT_DIRECT: "cost_direct_kernel<CW>", _lib.VARIANT_CELLS: "cost_cells_kernel<64,GAUSS,CW> (TILED32 gather)",
                            _lib.VARIANT_CELLS_NOREUSE: "cost_cells_kernel<64,GAUSS,CW,noreuse>",
                            _lib.VARIANT_TMA: "cost_tma_kernel<64,GAUSS,CW> (PIXC layout, TMA-staged window)"}.get(
                                variant, "cost_cells_kernel<64,GAUSS,CW> (TILED32 gather)"),

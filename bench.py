@@ -271,14 +271,18 @@ def main():
     variant = {"auto": _lib.VARIANT_AUTO, "direct": _lib.VARIANT_DIRECT, "cells": _lib.VARIANT_CELLS,
                "cells_noreuse": _lib.VARIANT_CELLS_NOREUSE, "tma": _lib.VARIANT_TMA}[args.variant]
 
-    inp = make_config(args.config, seed=1 + rank)
+    # Weak scaling = the SAME work on every GPU: all ranks build the same seeded batch (each owns its own copy).  With
+    # per-rank seeds the step time followed the poses drawn (the kernel's cost depends on how many bilinear cells a
+    # depth range crosses): +4 % on rank 1, +10 % on one of ranks 2-3 at the same 1965 MHz — that data variance, not
+    # the software, was the 0.91 "scaling efficiency" of round 1 (profiles/r2_scaling.md).
+    inp = make_config(args.config, seed=1)
     B, V, D = inp.B, inp.V, inp.D
     C, H, Wd = inp.ref_feat.shape[1], inp.ref_feat.shape[2], inp.ref_feat.shape[3]
     HW = H * Wd
     g = inp.to(dev)
     klist = [float(v) for v in inp.k.tolist()]
     karr = ops.k_array(klist)
-    gen = torch.Generator().manual_seed(5 + rank)
+    gen = torch.Generator().manual_seed(5)
     raw = (torch.randn(B, 2, H, Wd, generator=gen) * 0.1).to(dev)     # stand-in G-Net output (fixed)
     is_valid_d = inp.is_valid.to(dev)
     intM_d = inp.cam_intrins['intM'].to(dev)
@@ -324,10 +328,16 @@ def main():
         if sampler:
             sampler.stop()
         md.barrier()
-        return md.max_over_ranks(s.elapsed_time(e), device=dev)
+        own["ms"] = s.elapsed_time(e)
+        return md.max_over_ranks(own["ms"], device=dev)
 
+    own = {"ms": 0.0}
+    try:
+        full_affinity = os.sched_getaffinity(0)
+    except AttributeError:
+        full_affinity = None
     affinity = pin_to_gpu_cpus(local_rank)                           # each rank on the cores next to its GPU
-    sampler = ClockSampler(index=local_rank) if rank == 0 else None
+    sampler = ClockSampler(index=local_rank)                         # every rank watches its own GPU
     with torch.no_grad():
         for _ in range(W):
             hot_step()
@@ -350,6 +360,7 @@ def main():
         torch.cuda.synchronize()
         graph_ok = bool(torch.equal(graph_pred, eager_pred))
         ms_total = timed(graph.replay, K, sampler)
+        own_ms_step = own["ms"] / K
         launches = launches_per_step * K
         # spread: the same K-step region repeated (median / min / max of the max-over-ranks time per step)
         reps = sorted(timed(graph.replay, K) / K for _ in range(20))
@@ -358,11 +369,9 @@ def main():
     ms_step = ms_total / K
     frames_per_s = world * B * 1e3 / ms_step
     kern_ms = sum(a.elapsed_time(b) for a, b in ev_pairs) / max(1, len(ev_pairs))
-    repeats = {"regions": len(reps), "median_ms_per_step": reps[len(reps) // 2], "min_ms_per_step": reps[0],
-               "max_ms_per_step": reps[-1], "eager_ms_per_step": ms_eager, "graph_equals_eager": graph_ok,
-               "cpu_affinity": affinity}
-    if sampler and len(sampler.samples) < 5:
-        # timed region too short for the sampler: keep the identical load running while sampling
+    # per-rank view of the max-over-ranks number: this rank's own step time, cost-kernel time and SM clock under load.
+    # (No collective and one graph launch per step: what separates the ranks is the GPU each one runs on.)
+    if len(sampler.samples) < 5:
         with torch.no_grad():
             sampler.start()
             t_end = time.time() + 1.0
@@ -370,7 +379,13 @@ def main():
                 graph.replay()
             torch.cuda.synchronize()
             sampler.stop()
-
+    own_clock = sampler.report()
+    per_rank_rows = md.gather_over_ranks([own_ms_step, kern_ms, own_clock["sm_mhz"] or 0.0], device=dev)
+    per_rank = {"ms_per_step": [r[0] for r in per_rank_rows], "kernel_ms": [r[1] for r in per_rank_rows],
+                "sm_mhz_under_load": [r[2] for r in per_rank_rows]}
+    repeats = {"regions": len(reps), "median_ms_per_step": reps[len(reps) // 2], "min_ms_per_step": reps[0],
+               "max_ms_per_step": reps[-1], "eager_ms_per_step": ms_eager, "graph_equals_eager": graph_ok,
+               "cpu_affinity": affinity}
     # ---- loop including the real G-Net convolutions (PyTorch / cuDNN), reported beside the headline --------
     with_gnet = None
     if not args.no_gnet:
@@ -499,7 +514,8 @@ def main():
                                variant, "cost_cells_kernel<64,GAUSS,CW> (TILED32 gather)"),
                 "kernel_ms_how": "CUDA events around every cost-kernel launch of %d eager steps run right after the "
                                  "graph-replayed timed region (same kernels, arguments and buffers)" % min(K, 50),
-                "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src,
+                "kernel_ms": kern_ms, "kernel_ms_max_over_ranks": max(per_rank["kernel_ms"]),
+                "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src,
                 "launch": {"grid": grid, "block": block, "smem_bytes": smem}}
     # ---- reference-CUDA baseline (north_star / BASELINE.md §2): the reference's operator sequence (repeat,
     # grid_sample, mul, sum ... — ATen port, bit-identical to the reference on CPU) on the same B200, same inputs
@@ -546,6 +562,8 @@ def main():
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
+        if full_affinity is not None:
+            os.sched_setaffinity(0, full_affinity)                   # the CPU arm may use every host core again
         fps, info = cpu_reference_frames(args.config, steps=8, warmup=1, budget_s=20.0)
         cpu_baseline = {"value": fps, "unit": "frames/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
     line = {
@@ -557,9 +575,9 @@ def main():
                    "cache": "inputs_larger_than_l2 (%.0f MB resident per step vs 126 MB L2)" % ((abytes + 4 * V * B * C * HW) / 1e6),
                    "step": "repack + camera table + %d x (fused cost kernel + update kernel), one CUDA graph per rank, "
                            "K replays timed" % N_ITER},
-        "clocks": sampler.report() if sampler else None,
+        "clocks": own_clock,
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "reference_cuda": reference_cuda, "with_gnet": with_gnet, "repeats": repeats,
+        "reference_cuda": reference_cuda, "with_gnet": with_gnet, "repeats": repeats, "per_rank": per_rank,
         "gpu_launches_how": "%d kernels per step (counted by the library on an eager step) x %d graph replays" % (
             launches_per_step, K),
     }

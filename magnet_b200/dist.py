@@ -60,6 +60,18 @@ def sum_over_ranks(value: float, device=None) -> float:
     return float(t.item())
 
 
+def gather_over_ranks(values, device=None):
+    """Every rank's list of floats, as a list (one entry per rank) of lists — for per-rank diagnostics next to a
+    max-over-ranks number (which rank was the slow one, at which clock)."""
+    vals = [float(v) for v in values]
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [vals]
+    t = torch.tensor(vals, dtype=torch.float64, device=device or ("cuda" if dist.get_backend() == "nccl" else "cpu"))
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [[float(x) for x in o.tolist()] for o in out]
+
+
 def barrier() -> None:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()

@@ -456,6 +456,41 @@ def test_iteration_is_cuda_graph_capturable(cuda):
     assert torch.equal(cv, want)
 
 
+def test_drop_in_call_is_graph_capturable_and_repacks_inside_the_graph(cuda):
+    """the per-forward preparation cache keys on tensor versions, which a graph replay never bumps.
+    While a stream is capturing, est_costvolume_CW therefore bypasses the cache: repack + camera table become graph nodes
+    and a replay sees whatever the buffers hold.  (Inputs that live on the CPU cannot be uploaded during capture, so the
+    caller passes device-resident cam_intrins / is_valid — the reference's `.item()` on is_valid would not capture at all.)"""
+    inp = make_inputs(B=2, V=2, D=16, H=24, W=32, C=32, seed=93, depth="smooth")
+    g = inp.to(cuda)
+    cam_d = {k: v.to(cuda) for k, v in inp.cam_intrins.items()}
+    valid_d = inp.is_valid.to(cuda)
+    dvol = inp.depth_volume().to(cuda)
+    feat, gmm = g.nghbr_feat.clone(), g.nghbr_gmms.clone()
+    out = torch.empty_like(dvol)
+
+    def call():
+        out.copy_(magnet_b200.est_costvolume_CW(dvol, g.ref_feat, feat, g.ref_gmms, gmm, g.R, g.t, valid_d, cam_d, inp.thres))
+
+    call()                                                     # warm-up outside capture (function attributes, tensor map path)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            call()
+    torch.cuda.current_stream().wait_stream(side)
+    # refill the source buffers the way a replayed producer would: same tensor objects, new contents
+    feat.copy_(g.nghbr_feat.flip(0))
+    gmm.copy_(g.nghbr_gmms.flip(0))
+    graph.replay()
+    torch.cuda.synchronize()
+    want = magnet_b200.est_costvolume_CW(dvol, g.ref_feat, g.nghbr_feat.flip(0).contiguous(), g.ref_gmms,
+                                         g.nghbr_gmms.flip(0).contiguous(), g.R, g.t, valid_d, cam_d, inp.thres)
+    assert torch.equal(out, want), "the replayed graph must repack the refilled buffers, not serve a stale cache entry"
+
+
 def test_magnet_module_matches_reference_dataflow(cuda):
     """magnet_b200.MAGNET (reference forward signature, backbones injected) against the reference data flow
     (MAGNET.py:130-175) assembled from the ATen port on the same device, with small stand-in backbones."""

@@ -1,5 +1,5 @@
 #!/bin/bash
-# debug diagnostics + parity subset + kernel timings + ncu capture of the TMA kernel.  usage: gpu_quick2.sh <tag>
+# debug diagnostics + parity subset + kernel timings + ncu capture of the TMA kernel.  usage: gpu_kernel_visit.sh <tag>
 set -u
 TAG=${1:-q}; OUT=gpurun_out/$TAG; mkdir -p "$OUT"
 timeout 300 python scripts/debug_tma.py > $OUT/staged.txt 2>&1; echo "debug rc=$?"; grep "^\[" $OUT/staged.txt

@@ -128,7 +128,7 @@ struct LaneCells {
 __device__ __forceinline__ LaneCells phase_a(const ViewGeom& g, const uint32_t tm, const int mend, const int nj,
                                              const int jb, const int jlo, const int Dc, const int W, const int H,
                                              const int lane, const int pxl, float2* __restrict__ stg,
-                                             float2* __restrict__ org, int (&box)[4], bool& complete) {
+                                             float2* __restrict__ org, int (&box)[4]) {
   const unsigned FULL = 0xffffffffu;
   const int h = lane >> 3;
   const float xmax = (float)W + 1.0f, ymax = (float)H + 1.0f;
@@ -203,9 +203,7 @@ __device__ __forceinline__ LaneCells phase_a(const ViewGeom& g, const uint32_t t
   int base = incl - n;
   const int kept_g = max(0, min(n, NORG - base));
   int jstop = Dc;
-  complete = true;
   if (__any_sync(FULL, kept_g < n || lane_stop < nj)) {   // some lane of the warp has to drop cells: rare
-    complete = false;                                     // (dropped cells are not in the bounding box)
     int js = Dc;
     if (kept_g < n) js = jb + (int)__fns(mask, 0, kept_g + 1);   // my first dropped start
     else if (lane_stop < nj) js = jb + lane_stop;
@@ -519,8 +517,7 @@ cost_tma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
 
     // ---------------- phase A + bounding box of the CTA's cells ---------------------------------------------
     int box[4];
-    bool complete;
-    LaneCells lc = phase_a(g, tm, mend, nj, jb, 0, Dc, W, H, lane, pxl, stg, org, box, complete);
+    LaneCells lc = phase_a(g, tm, mend, nj, jb, 0, Dc, W, H, lane, pxl, stg, org, box);
     int* bb = bbox + (it & 1) * 4;
     if (lane == 0) {
       atomicMin(bb + 0, box[0]); atomicMax(bb + 1, box[1]); atomicMin(bb + 2, box[2]); atomicMax(bb + 3, box[3]);
@@ -572,7 +569,8 @@ cost_tma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
       }
       if (!__any_sync(FULL, lc.jstop < Dc)) break;
       jlo = lc.jstop;                                      // restart the walk behind the last covered hypothesis;
-      lc = phase_a(g, tm, mend, nj, jb, jlo, Dc, W, H, lane, pxl, stg, org, box, complete);   // taps from global memory
+      lc = phase_a(g, tm, mend, nj, jb, jlo, Dc, W, H, lane, pxl, stg, org, box);   // (the window only covers the
+                                                                                      //  first walk's cells: global taps)
     }
   }
 

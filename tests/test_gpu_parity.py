@@ -76,6 +76,42 @@ def test_cw_vs_oracle_seeded(cuda, seed, depth, shape):
     compare_volume(got, want, margin, what=f"seed{seed}/auto")
 
 
+def test_tma_kernel_fuzz_against_direct_kernel(cuda):
+    """Randomised shapes / poses for the TMA-staged kernel against the reference-order direct kernel (both depth modes):
+    ragged tiles, 1..6 views with invalid ones, 1..150 planes (1..3 chunks, partial lane quarters), large baselines (windows
+    that do not fit -> global tap path), random depths (more than 16 cells per pixel -> walk restarts), both families.
+    No oracle here, so elements on the consistency threshold are budgeted instead of margin-checked."""
+    rng = np.random.default_rng(2024)
+    worst = 0.0
+    for it in range(24):
+        C = int(rng.choice([16, 32, 64]))
+        B, V = int(rng.integers(1, 3)), int(rng.integers(1, 7))
+        D = int(rng.choice([1, 3, 5, 17, 33, 64, 65, 150])) if it % 3 else int(rng.integers(1, 70))
+        H, W = int(rng.integers(5, 41)), int(rng.integers(5, 71))
+        depth = "random" if it % 4 == 0 else "smooth"
+        family = "kitti" if it % 5 == 0 else "scannet"
+        kw = dict(rot_deg=float(rng.uniform(1, 14)), trans=float(rng.uniform(0.05, 0.7))) if it % 2 else {}
+        invalid = [(0, int(rng.integers(0, V)))] if V > 1 and it % 3 == 0 else ()
+        inp = make_inputs(B=B, V=V, D=D, H=H, W=W, C=C, seed=1000 + it, depth=depth, family=family, invalid=invalid, **kw)
+        g = inp.to(cuda)
+        plan = magnet_b200.MatchingPlan(g.ref_feat, g.nghbr_feat, g.nghbr_gmms, g.nghbr_poses, inp.is_valid,
+                                        inp.cam_intrins, thres=inp.thres)
+        k = inp.k.tolist()
+        want = plan.cost(g.ref_gmms, k, variant=_lib.VARIANT_DIRECT)
+        dvol = ops.sample_depths(g.ref_gmms, k)
+        for mode, got in (("fused", plan.cost(g.ref_gmms, k, variant=_lib.VARIANT_TMA)),
+                          ("drop-in", magnet_b200.est_costvolume_CW(dvol, g.ref_feat, g.nghbr_feat, g.ref_gmms, g.nghbr_gmms,
+                                                                      g.R, g.t, inp.is_valid, inp.cam_intrins, inp.thres,
+                                                                      variant=_lib.VARIANT_TMA))):
+            assert torch.isfinite(got).all(), (it, mode)
+            scale = max(float(want.abs().max()), 1e-20)
+            d = (got - want).abs()
+            frac = float((d > 1e-4 * scale).float().mean())
+            worst = max(worst, frac)
+            assert frac <= 2e-3 and float(d.median()) <= 1e-5 * scale, (it, mode, dict(B=B, V=V, D=D, H=H, W=W, C=C, depth=depth), frac)
+    print("fuzz: worst fraction of threshold-adjacent elements", worst)
+
+
 def test_fused_sampler_equals_drop_in(cuda):
     """MAGNET_DEPTH_GAUSS (sampler fused, analytic cell walk) against MAGNET_DEPTH_VOLUME (drop-in, exact
     per-hypothesis cell walk): d_j is formed with the same separately rounded multiply and add (MAGNET.py:155);

@@ -205,11 +205,9 @@ cost_cells_kernel(const __grid_constant__ CostParams p, const int chunk, const i
         const float4* rp = rec + tid - 3 * NT;
         float* ap = acc + (j_lo - jc) * NT + tid;
         unsigned starts = startmask >> (j_lo - jc);                      // bit 0 <=> hypothesis j starts a cell
-#pragma unroll 4
-        for (int j = j_lo; j < j_end; ++j, ap += NT, starts >>= 1) {
-          float ix, iy, z;
-          project(depth_of<MODE>(p, ds, j), a0, a1, a2, q0, q1, q2, ix, iy, z);
-          if (starts & 1u) {                                             // entering the lane's next cell
+        // one hypothesis: switch to the lane's next cell where the mask says so, blend, test, accumulate
+        auto eval = [&](const float ix, const float iy, const float z, const bool start, float* __restrict__ a) {
+          if (start) {                                                   // entering the lane's next cell
             hp += NT;
             rp += 3 * NT;
             const float2 h = *hp;
@@ -231,7 +229,20 @@ cost_cells_kernel(const __grid_constant__ CostParams p, const int chunk, const i
             // homography.py:157-158: |z - mu~| < sigma~ * kappa, strict
             val = (fabsf(__fsub_rn(z, mu)) < __fmul_rn(sg, p.kappa)) ? cost : 0.0f;
           }
-          *ap += val;
+          *a += val;
+        };
+        int j = j_lo;
+#pragma unroll 2
+        for (; j + 1 < j_end; j += 2, ap += 2 * NT, starts >>= 2) {      // two hypotheses per packed (f32x2) projection
+          float2 ix2, iy2, z2;
+          project2(make_float2(depth_of<MODE>(p, ds, j), depth_of<MODE>(p, ds, j + 1)), a0, a1, a2, q0, q1, q2, ix2, iy2, z2);
+          eval(ix2.x, iy2.x, z2.x, (starts & 1u) != 0u, ap);
+          eval(ix2.y, iy2.y, z2.y, (starts & 2u) != 0u, ap + NT);
+        }
+        if (j < j_end) {
+          float ix, iy, z;
+          project(depth_of<MODE>(p, ds, j), a0, a1, a2, q0, q1, q2, ix, iy, z);
+          eval(ix, iy, z, (starts & 1u) != 0u, ap);
         }
       }
       j_lo = j_end;

@@ -73,24 +73,8 @@ struct ViewGeom {
   float a0, a1, a2, q0, q1, q2;
 };
 
-__device__ __forceinline__ float rcp_approx(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-
-// Two hypotheses at once (packed f32x2): continuous sample position (ix, iy) = projected pixel - 0.5 and source-camera
-// depth z.  Elementwise the same operations as cells_common.cuh: project() (z = a2 + q2*d separately rounded).
 __device__ __forceinline__ void project2(const float2 d, const ViewGeom& g, float2& ix, float2& iy, float2& z) {
-  const float2 P0 = __ffma2_rn(make_float2(g.q0, g.q0), d, make_float2(g.a0, g.a0));
-  const float2 P1 = __ffma2_rn(make_float2(g.q1, g.q1), d, make_float2(g.a1, g.a1));
-  z = __fadd2_rn(make_float2(g.a2, g.a2), __fmul2_rn(make_float2(g.q2, g.q2), d));
-  const float2 zp = __fadd2_rn(z, make_float2(1e-10f, 1e-10f));
-  float2 r = make_float2(rcp_approx(zp.x), rcp_approx(zp.y));
-  const float2 e = __ffma2_rn(make_float2(-zp.x, -zp.y), r, make_float2(1.0f, 1.0f));
-  r = __ffma2_rn(r, e, r);
-  ix = __ffma2_rn(P0, r, make_float2(-0.5f, -0.5f));
-  iy = __ffma2_rn(P1, r, make_float2(-0.5f, -0.5f));
+  project2(d, g.a0, g.a1, g.a2, g.q0, g.q1, g.q2, ix, iy, z);   // common.cuh: two hypotheses per packed instruction
 }
 
 // predicated shared-memory loads (the destination keeps its value when the predicate is false): phase C reloads the

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MAGNET_ABI_VERSION 2
+#define MAGNET_ABI_VERSION 3
 #define MAGNET_MAX_PLANES 256   /* max depth hypotheses / planes per call (D) */
 
 typedef enum magnet_status {
@@ -50,23 +50,30 @@ typedef enum magnet_src_layout {
   MAGNET_SRC_TILED32 = 1, /* (V*B, H, ceil(W/32), C/4, 32, 4): per row, tiles of 32 pixels; inside a tile
                             the C/4 channel quads are 512 B apart and the 32 pixels of one quad are
                             contiguous (see magnet_repack_tiled32_f32).  Pixels x >= W are padding. */
-  MAGNET_SRC_PIXC = 2     /* (V*B, H, W, C+4): pixel-major, per pixel the C channels followed by the source
+  MAGNET_SRC_PIXC = 2,    /* (V*B, H, W, C+4): pixel-major, per pixel the C channels followed by the source
                             Gaussian (mu, sigma) and two zeros (see magnet_repack_pixc_f32): the layout the
                             TMA-staged production kernel fetches its windows from.  With this layout
                             magnet_cost_args.src_gmm is ignored (the Gaussians travel inside src_feat). */
+  MAGNET_SRC_SPLIT16 = 3  /* tensor-core layout (C == 64): a 256-byte header (power-of-two scale s), two fp16 planes
+                            (V*B, 2, H, W, 64) with x*s = hi + lo, and a (V*B, H, W, 4) table (mu, sigma, 0, 0); see
+                            magnet_repack_split16_f32 / magnet_split16_bytes.  With this layout ref_feat must ALSO
+                            point to a split buffer (of the B reference feature maps, Gaussians NULL) and src_gmm is
+                            ignored. */
 } magnet_src_layout;
 
 /* Kernel selection (for parity cross-checks and profiling). */
 typedef enum magnet_variant {
-  MAGNET_VARIANT_AUTO = 0,   /* production choice: TMA for MAGNET_SRC_PIXC, CELLS for MAGNET_SRC_TILED32,
-                                DIRECT otherwise                                               */
+  MAGNET_VARIANT_AUTO = 0,   /* production choice: MMA for MAGNET_SRC_SPLIT16, TMA for MAGNET_SRC_PIXC, CELLS for
+                                MAGNET_SRC_TILED32, DIRECT otherwise                           */
   MAGNET_VARIANT_DIRECT = 1, /* one thread per output, 4 taps x C channels per hypothesis,
                                 reference operation order, fp64 view accumulation             */
   MAGNET_VARIANT_CELLS = 2,  /* tap-sharing kernel: per-lane bilinear-cell records             */
   MAGNET_VARIANT_CELLS_NOREUSE = 3, /* diagnostic: as CELLS, but every cell gathers all 4 taps
                                        (MAGNET_DEPTH_GAUSS only)                               */
-  MAGNET_VARIANT_TMA = 4     /* production: tap-sharing kernel, 4 lanes per pixel, the CTA's source window
+  MAGNET_VARIANT_TMA = 4,    /* production: tap-sharing kernel, 4 lanes per pixel, the CTA's source window
                                 staged in shared memory by TMA (MAGNET_SRC_PIXC only)          */
+  MAGNET_VARIANT_MMA = 5     /* tensor-core kernel: all (reference pixel, window cell) channel dot products of an
+                                8x8 tile by tcgen05.mma into tensor memory (MAGNET_SRC_SPLIT16 only) */
 } magnet_variant;
 
 /* Per (batch element, view) camera constants, 16 floats, produced by magnet_pack_cameras_f32.
@@ -93,7 +100,7 @@ typedef struct magnet_cost_args {
   int32_t softmax;         /* 1: softmax over the D planes after the 1/V mean (est_costvolume_F)*/
   int32_t variant;         /* magnet_variant                                                    */
   float kappa;             /* 'thres' of est_costvolume_CW (float(int))                         */
-  const float* ref_feat;   /* (B, C, H, W) NCHW                                                 */
+  const float* ref_feat;   /* (B, C, H, W) NCHW; a split buffer with MAGNET_SRC_SPLIT16           */
   const float* src_feat;   /* (V*B, ...) view-major, layout = src_layout                        */
   const float* src_gmm;    /* (V*B, 2, H, W) [mu, sigma]; required when consistency == 1        */
   const float* rays;       /* (B, 3, H*W) 'unit_ray_array_2D'                                   */
@@ -151,6 +158,13 @@ int magnet_pack_cameras_f32(const float* intM, const float* R, int64_t r_sb, int
  * N_iter iterations, MAGNET.py:150-169). */
 int magnet_repack_pixc_f32(const float* src_nchw, const float* src_gmm, float* dst, int32_t N, int32_t C, int32_t H,
                            int32_t W, void* stream);
+
+/* Feature split (N, 64, H, W) features [+ (N, 2, H, W) Gaussians, may be NULL -> zeros] -> MAGNET_SRC_SPLIT16 buffer of
+ * magnet_split16_bytes(N, H, W) bytes; src and dst 16-byte aligned.  Three stream operations (header memset, max |x|
+ * reduction, split).  Once per forward for the source views and once for the reference features. */
+size_t magnet_split16_bytes(int32_t N, int32_t H, int32_t W);
+int magnet_repack_split16_f32(const float* src_nchw, const float* src_gmm, void* dst, int32_t N, int32_t C, int32_t H,
+                              int32_t W, void* stream);
 
 /* Source-feature repack (N, C, H, W) -> MAGNET_SRC_TILED32 (N, H, ceil(W/32), C/4, 32, 4);
  * C % 4 == 0, dst 16-byte aligned, padding pixels are written as zeros. */

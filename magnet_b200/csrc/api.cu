@@ -15,6 +15,15 @@ bool cells_supports(int C, int D, int layout);
 cudaError_t launch_cost_tma(const CostParams& p, int mode, int C, bool cw, cudaStream_t st);
 bool tma_supports(int C, int D, int V, int layout);
 void tma_launch_info(int B, int H, int W, int D, int* grid, int* block, int* smem);
+cudaError_t launch_cost_mma(const CostParams& p, int mode, bool cw, cudaStream_t st);
+bool mma_supports(int C, int D, int V, int layout);
+void mma_launch_info(int B, int H, int W, int D, int* grid, int* block, int* smem);
+size_t split16_buffer_bytes(int N, int H, int W);
+cudaError_t launch_repack_split16(const float* src, const float* gmm, void* dst, int N, int C, int H, int W,
+                                  cudaStream_t st, int* launches);
+#ifdef MAGNET_MMA_DEBUG
+void mma_set_debug_buffer(float* p);
+#endif
 cudaError_t launch_repack_pixc(const float* src, const float* gmm, float* dst, int N, int C, int H, int W,
                                cudaStream_t st);
 void cells_launch_info(int B, int H, int W, int D, int* grid, int* block, int* smem);
@@ -56,7 +65,8 @@ int validate_cost(const magnet_cost_args* a) {
   if (a->D > MAGNET_MAX_PLANES) return MAGNET_ERR_UNSUPPORTED;
   if ((int64_t)a->H * a->W > (1 << 26)) return MAGNET_ERR_SHAPE;
   if (!a->ref_feat || !a->src_feat || !a->rays || !a->cams || !a->out) return MAGNET_ERR_NULL;
-  if (a->consistency && !a->src_gmm && a->src_layout != MAGNET_SRC_PIXC) return MAGNET_ERR_NULL;
+  if (a->consistency && !a->src_gmm && a->src_layout != MAGNET_SRC_PIXC && a->src_layout != MAGNET_SRC_SPLIT16)
+    return MAGNET_ERR_NULL;
   if (a->consistency && a->softmax) return MAGNET_ERR_UNSUPPORTED;
   switch (a->depth_mode) {
     case MAGNET_DEPTH_VOLUME: if (!a->d_volume) return MAGNET_ERR_NULL; break;
@@ -71,10 +81,17 @@ int validate_cost(const magnet_cost_args* a) {
     if (!magnet::tma_supports(a->C, a->D, a->V, a->src_layout)) return MAGNET_ERR_UNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(a->src_feat) % 16 != 0) return MAGNET_ERR_ALIGN;
     if (a->variant != MAGNET_VARIANT_AUTO && a->variant != MAGNET_VARIANT_TMA) return MAGNET_ERR_UNSUPPORTED;
+  } else if (a->src_layout == MAGNET_SRC_SPLIT16) {
+    if (!magnet::mma_supports(a->C, a->D, a->V, a->src_layout)) return MAGNET_ERR_UNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(a->src_feat) % 16 != 0 || reinterpret_cast<uintptr_t>(a->ref_feat) % 16 != 0)
+      return MAGNET_ERR_ALIGN;
+    if (a->variant != MAGNET_VARIANT_AUTO && a->variant != MAGNET_VARIANT_MMA) return MAGNET_ERR_UNSUPPORTED;
   } else if (a->src_layout != MAGNET_SRC_NCHW) {
     return MAGNET_ERR_UNSUPPORTED;
   }
-  if (a->variant < MAGNET_VARIANT_AUTO || a->variant > MAGNET_VARIANT_TMA) return MAGNET_ERR_UNSUPPORTED;
+  if (a->variant < MAGNET_VARIANT_AUTO || a->variant > MAGNET_VARIANT_MMA) return MAGNET_ERR_UNSUPPORTED;
+  if (a->variant == MAGNET_VARIANT_MMA && !magnet::mma_supports(a->C, a->D, a->V, a->src_layout))
+    return MAGNET_ERR_UNSUPPORTED;
   if (a->variant == MAGNET_VARIANT_TMA && !magnet::tma_supports(a->C, a->D, a->V, a->src_layout))
     return MAGNET_ERR_UNSUPPORTED;
   if ((a->variant == MAGNET_VARIANT_CELLS || a->variant == MAGNET_VARIANT_CELLS_NOREUSE) &&
@@ -85,12 +102,17 @@ int validate_cost(const magnet_cost_args* a) {
 }
 
 bool use_cells(const magnet_cost_args* a) {
-  if (a->variant == MAGNET_VARIANT_DIRECT || a->variant == MAGNET_VARIANT_TMA) return false;
+  if (a->variant == MAGNET_VARIANT_DIRECT || a->variant == MAGNET_VARIANT_TMA || a->variant == MAGNET_VARIANT_MMA)
+    return false;
   return magnet::cells_supports(a->C, a->D, a->src_layout);
 }
 
 bool use_tma(const magnet_cost_args* a) {                  // the PIXC layout is served by the TMA kernel only
   return a->src_layout == MAGNET_SRC_PIXC && magnet::tma_supports(a->C, a->D, a->V, a->src_layout);
+}
+
+bool use_mma(const magnet_cost_args* a) {                  // the SPLIT16 layout is served by the tensor-core kernel only
+  return a->src_layout == MAGNET_SRC_SPLIT16 && magnet::mma_supports(a->C, a->D, a->V, a->src_layout);
 }
 }  // namespace
 
@@ -118,7 +140,9 @@ int magnet_cost_launch_info(const magnet_cost_args* a, int* grid_ctas, int* bloc
   const int st = validate_cost(a);
   if (st != MAGNET_OK) return st;
   if (!grid_ctas || !block_threads || !smem_bytes) return MAGNET_ERR_NULL;
-  if (use_tma(a)) {
+  if (use_mma(a)) {
+    magnet::mma_launch_info(a->B, a->H, a->W, a->D, grid_ctas, block_threads, smem_bytes);
+  } else if (use_tma(a)) {
     magnet::tma_launch_info(a->B, a->H, a->W, a->D, grid_ctas, block_threads, smem_bytes);
   } else if (use_cells(a)) {
     magnet::cells_launch_info(a->B, a->H, a->W, a->D, grid_ctas, block_threads, smem_bytes);
@@ -147,8 +171,10 @@ int magnet_cost_volume_f32(const magnet_cost_args* a, void* stream) {
     if (!(p.k[j] >= p.k[j - 1])) p.k_sorted = 0;
   int launches = 0;
   cudaError_t e;
-  if (use_tma(a) || use_cells(a)) {
-    if (use_tma(a))
+  if (use_mma(a) || use_tma(a) || use_cells(a)) {
+    if (use_mma(a))
+      e = magnet::launch_cost_mma(p, a->depth_mode, a->consistency != 0, (cudaStream_t)stream);
+    else if (use_tma(a))
       e = magnet::launch_cost_tma(p, a->depth_mode, a->C, a->consistency != 0, (cudaStream_t)stream);
     else
       e = magnet::launch_cost_cells(p, a->depth_mode, a->C, a->consistency != 0,
@@ -228,6 +254,28 @@ int magnet_repack_pixc_f32(const float* src_nchw, const float* src_gmm, float* d
   g_launches += 1;
   return MAGNET_OK;
 }
+
+size_t magnet_split16_bytes(int32_t N, int32_t H, int32_t W) {
+  if (N <= 0 || H <= 0 || W <= 0) return 0;
+  return magnet::split16_buffer_bytes(N, H, W);
+}
+
+int magnet_repack_split16_f32(const float* src_nchw, const float* src_gmm, void* dst, int32_t N, int32_t C, int32_t H,
+                              int32_t W, void* stream) {
+  if (!src_nchw || !dst) return MAGNET_ERR_NULL;
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || N > 65535) return MAGNET_ERR_SHAPE;
+  if (C != 64) return MAGNET_ERR_UNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(dst) % 16 != 0 || reinterpret_cast<uintptr_t>(src_nchw) % 16 != 0) return MAGNET_ERR_ALIGN;
+  int launches = 0;
+  cudaError_t e = magnet::launch_repack_split16(src_nchw, src_gmm, dst, N, C, H, W, (cudaStream_t)stream, &launches);
+  if (e != cudaSuccess) return cuda_fail(e);
+  g_launches += launches;
+  return MAGNET_OK;
+}
+
+#ifdef MAGNET_MMA_DEBUG
+void magnet_mma_debug_buffer(float* p) { magnet::mma_set_debug_buffer(p); }
+#endif
 
 int magnet_sample_depths_f32(const float* gmm, const float* k_host, int32_t B, int32_t D, int32_t HW,
                              float* d_volume, void* stream) {

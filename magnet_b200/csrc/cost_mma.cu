@@ -1,0 +1,589 @@
+// MAGNET_VARIANT_MMA — tensor-core kernel: fused warp + sample + consistency + view fusion with the channel dot
+// products of a whole (tile, view) computed by tcgen05.mma into tensor memory.
+//
+// Replaces homography.py:79-161 (and :10-75 with CW == false); absorbs the sampler of MAGNET.py:154-156.
+//
+// Identity: sum_c ref_c (sum_t w_t src_tc) = sum_t w_t <ref, src_t>.  cost_cells.cu / cost_tma.cu find, per pixel, the
+// ~6 bilinear cells its hypotheses visit and compute <ref, src_t> for exactly those taps on the CUDA cores — the
+// bookkeeping (cell walk, records, lockstep over cells) costs 3x the instructions of the arithmetic.  Here the dot
+// products of ALL (reference pixel, window cell) pairs of an 8x8 tile are one small GEMM,
+//        G[p][c] = <ref_p, src_c>,  64 pixels x (<= 256 window cells) x 64 channels,
+// ~12x more products than needed but on the tensor pipe, which is otherwise idle; what remains per hypothesis is the
+// projection, four G[p][c] + four (mu, sigma)[c] shared-memory reads and three bilinear interpolations.
+//
+//   * fp32 accuracy on fp16 tensor cores: every feature map is split once per forward into x*s = hi + lo (two fp16
+//     planes, s a power of two that maps max|x| into [2^14, 2^15)); hi*hi + hi*lo + lo*hi carries 22 significant bits
+//     per factor, products are exact in the fp32 accumulator (MAGNET_SRC_SPLIT16, magnet_repack_split16_f32).
+//   * the planes are (image, plane, y, x, 64 channels) fp16 = 128-byte rows: an 8-pixel TMA box with
+//     CU_TENSOR_MAP_SWIZZLE_128B lands as one canonical K-major UMMA atom per plane; the window of a (tile, view) is the
+//     bounding box of the tile's sample positions cut into such 8-cell segments (zero fill outside the image =
+//     grid_sample's padding_mode='zeros'), cell index = B-operand row = accumulator column.  The reference tile is the
+//     A operand (rows 0..63 of an M = 128 instruction; rows 64..127 read whatever follows and are never looked at).
+//   * one warp per reference pixel, one LANE per hypothesis (two hypotheses per lane for a 64-hypothesis chunk): the
+//     pixel's constants are warp-uniform, the 32 lanes read a handful of neighbouring cells of ONE accumulator row
+//     (broadcast / conflict-free), the accumulators over the views stay in registers.
+//   * per view: project all hypotheses (bounding box per 32-hypothesis block) -> TMA window + (mu, sigma) table ->
+//     12 x tcgen05.mma (3 products x 4 K steps) -> tcgen05.ld the 64 accumulator rows into shared memory (over the
+//     window, which is dead by then) -> per-hypothesis phase.  Two CTAs per SM overlap each other's copy / MMA latency.
+//     A window that does not fit 256 cells is split into its two 32-hypothesis blocks; a block that still does not fit
+//     (incoherent depths) takes its taps from global memory, one hypothesis at a time across the warp.  Always correct.
+//
+// Numerics: the per-view channel sum is the tensor core's fp32 accumulation of exact products of the split factors
+// (relative error ~2^-21 of sum |ref||src|, the same order as an fp32 FMA chain); everything else — projection, weights,
+// consistency test, view accumulation, 1/V — is the fp32 arithmetic of the other kernels (common.cuh project2).
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstddef>
+#include <mutex>
+
+#include "common.cuh"
+#include "tma_common.cuh"
+
+namespace magnet {
+
+constexpr int MNT = 256;               // threads per CTA: warp w owns tile row w, pixel i of the row in turn
+constexpr int MTW = 8, MTH = 8;        // CTA tile in reference pixels
+constexpr int MPX = MTW * MTH;         // 64 = rows of the accumulator that are used
+constexpr int MCH = 64;                // hypotheses per CTA (two per lane)
+constexpr int MSEG = 32;               // 8-cell segments per window: N <= 256 accumulator columns
+constexpr int MMAXV = 16;              // views whose camera constants are staged in shared memory
+constexpr int M_TMEM_COLS = 256;
+constexpr int SEG_BYTES = 2048;        // hi atom (8 cells x 128 B) + lo atom
+constexpr int META_SEG_BYTES = 128;    // 8 cells x (mu, sigma, 0, 0)
+
+// shared-memory map (bytes from the 1024-aligned base)
+constexpr int MOFF_A = 0;                                   // reference tile: hi 8 KB | lo 8 KB
+constexpr int MOFF_R = 16384;                               // window segments, later the accumulator rows G[64][GP]
+constexpr int MR_BYTES = 67584;                             //   >= 32 * 2048 and >= 64 * 260 * 4
+constexpr int MOFF_META = MOFF_R + MR_BYTES;                // float4[256] (mu, sigma, 0, 0) per window cell
+constexpr int MOFF_CAM = MOFF_META + MSEG * META_SEG_BYTES; // magnet_camera[MMAXV]
+constexpr int MOFF_KS = MOFF_CAM + MMAXV * 64;              // float[MCH]
+constexpr int MOFF_BBOX = MOFF_KS + MCH * 4;                // int[2 slots][4]
+constexpr int MOFF_BAR = MOFF_BBOX + 64;                    // 2 mbarriers, TMEM base address
+constexpr int M_SMEM_USED = MOFF_BAR + 32;
+constexpr int M_SMEM_TOTAL = M_SMEM_USED + 1024;            // slack for the 1024-byte alignment of the base
+static_assert(MR_BYTES >= MSEG * SEG_BYTES && MR_BYTES >= MPX * 260 * 4 && MR_BYTES >= MCH * 65 * 4, "region R");
+static_assert(2 * (M_SMEM_TOTAL + 1024) <= 228 * 1024, "two CTAs per SM");
+
+// header of a MAGNET_SRC_SPLIT16 buffer (256 bytes)
+struct Split16Header {
+  float scale;       // s = 2^k
+  float inv_scale;   // 2^-k
+  unsigned absmax;   // bits of max |x|
+};
+constexpr size_t SPLIT16_HEADER = 256;
+
+__host__ __device__ inline size_t split16_bytes(size_t N, size_t HW) { return SPLIT16_HEADER + N * HW * (256 + 16); }
+
+__device__ __forceinline__ void mbar_wait_or_trap(uint32_t bar, uint32_t parity) {
+  // bounded spin: a protocol error must surface as a launch failure, not as a hung GPU
+#pragma unroll 1
+  for (int it = 0; it < (1 << 24); ++it) {
+    uint32_t done;
+    asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
+__device__ __forceinline__ float lerp2d(float v00, float v01, float v10, float v11, float fx, float fy) {
+  const float t = __fmaf_rn(fx, v01 - v00, v00), u = __fmaf_rn(fx, v11 - v10, v10);
+  return __fmaf_rn(fy, u - t, t);
+}
+
+// shared-memory loads by 32-bit shared address (the window / table offsets are computed as integers)
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f32x2(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+// bilinear interpolation of a (mu, sigma) pair with packed f32x2 instructions; v01 - v00 as fma(v00, -1, v01) (exact
+// product, one rounding = the subtraction)
+__device__ __forceinline__ float2 lerp2d_x2(float2 v00, float2 v01, float2 v10, float2 v11, float fx, float fy) {
+  const float2 m1 = make_float2(-1.0f, -1.0f), fx2 = make_float2(fx, fx), fy2 = make_float2(fy, fy);
+  const float2 t = __ffma2_rn(fx2, __ffma2_rn(v00, m1, v01), v00), u = __ffma2_rn(fx2, __ffma2_rn(v10, m1, v11), v10);
+  return __ffma2_rn(fy2, __ffma2_rn(t, m1, u), t);
+}
+
+template <int MODE, bool CW>
+__global__ void __launch_bounds__(MNT, 2)
+cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CUtensorMap tm_ref,
+                const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_meta, const int nchunks,
+                float* __restrict__ dbg) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t padb = (1024u - (raw & 1023u)) & 1023u;
+  unsigned char* smem = smem_raw + padb;
+  const uint32_t sbase = raw + padb;
+  const magnet_camera* cams_s = reinterpret_cast<const magnet_camera*>(smem + MOFF_CAM);
+  float* ks = reinterpret_cast<float*>(smem + MOFF_KS);
+  int* bbox = reinterpret_cast<int*>(smem + MOFF_BBOX);
+  float* regR = reinterpret_cast<float*>(smem + MOFF_R);
+  const uint32_t bar_tma = sbase + MOFF_BAR, bar_mma = sbase + MOFF_BAR + 8;
+  const unsigned FULL = 0xffffffffu;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y;
+  const int H = p.H, W = p.W, HW = p.HW, D = p.D, V = p.V;
+  const int tiles_x = (W + MTW - 1) / MTW;
+  const int tile = blockIdx.x / nchunks;
+  const int jc = (blockIdx.x % nchunks) * MCH;
+  const int Dc = min(MCH, D - jc);
+  const int tx0 = (tile % tiles_x) * MTW, ty0 = (tile / tiles_x) * MTH;
+  const bool act0 = lane < Dc, act1 = lane + 32 < Dc;
+
+  const unsigned char* refbuf = reinterpret_cast<const unsigned char*>(p.ref_feat);
+  const unsigned char* srcbuf = reinterpret_cast<const unsigned char*>(p.src_feat);
+  const Split16Header* hdr_ref = reinterpret_cast<const Split16Header*>(refbuf);
+  const Split16Header* hdr_src = reinterpret_cast<const Split16Header*>(srcbuf);
+
+  if (warp == 0) tmem_alloc(sbase + MOFF_BAR + 16, M_TMEM_COLS);
+  if (tid == 0) {
+    mbar_init(bar_tma, 1);
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+    prefetch_tmap(&tm_ref);
+    prefetch_tmap(&tm_src);
+    prefetch_tmap(&tm_meta);
+  }
+  if (tid < 8) bbox[tid] = (tid & 1) ? -(1 << 28) : (1 << 28);       // [slot][x_lo, x_hi, y_lo, y_hi]
+  if (tid < MCH) ks[tid] = (MODE != MAGNET_DEPTH_VOLUME && jc + tid < D) ? p.k[jc + tid] : 0.0f;
+  tmem_fence_before_sync();
+  __syncthreads();
+  tmem_fence_after_sync();
+  if (tid == 0) {                                          // camera table of the batch element + the reference tile
+    mbar_arrive_expect_tx(bar_tma, (uint32_t)V * 64u + 16384u);
+    bulk_load(sbase + MOFF_CAM, p.cams + (size_t)b * V, (uint32_t)V * 64u, bar_tma);
+    tma_load_5d(sbase + MOFF_A, &tm_ref, bar_tma, 0, tx0, ty0, 0, b);
+  }
+  const uint32_t tmem_base = *reinterpret_cast<const volatile uint32_t*>(smem + MOFF_BAR + 16);
+
+  // ---- per-warp constants: lane i (mod 8) holds the ray / Gaussian of pixel i of my tile row ----------------
+  const int py = ty0 + warp;
+  float R0, R1, R2, MU = 0.f, SG = 0.f;
+  unsigned livemask;
+  {
+    const int px = tx0 + (lane & 7);
+    const bool live = px < W && py < H;
+    const int n = min(py, H - 1) * W + min(px, W - 1);     // dead pixels shadow the nearest pixel, never store
+    R0 = ldg_f(p.rays + ((size_t)b * 3 + 0) * HW + n);
+    R1 = ldg_f(p.rays + ((size_t)b * 3 + 1) * HW + n);
+    R2 = ldg_f(p.rays + ((size_t)b * 3 + 2) * HW + n);
+    if (MODE == MAGNET_DEPTH_GAUSS) {
+      MU = ldg_f(p.ref_gmm + ((size_t)b * 2 + 0) * HW + n);
+      SG = ldg_f(p.ref_gmm + ((size_t)b * 2 + 1) * HW + n);
+    }
+    livemask = __ballot_sync(FULL, live) & 0xffu;
+  }
+  // my two hypotheses of every pixel of the row: d[i] = (hypothesis jc + lane, hypothesis jc + 32 + lane)
+  float2 d[MTW];
+  if (MODE == MAGNET_DEPTH_VOLUME) {                       // coalesced read, transposed through shared memory
+    for (int idx = tid; idx < MCH * MPX; idx += MNT) {
+      const int j = idx >> 6, pp = idx & 63;
+      const int y = ty0 + (pp >> 3), x = tx0 + (pp & 7);
+      float v = 0.0f;
+      if (j < Dc && x < W && y < H) v = ldg_f(p.d_volume + ((size_t)b * D + jc + j) * HW + (size_t)y * W + x);
+      regR[j * 65 + pp] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < MTW; ++i) d[i] = make_float2(regR[lane * 65 + warp * 8 + i], regR[(lane + 32) * 65 + warp * 8 + i]);
+    fence_proxy_async();
+    __syncthreads();
+  } else {
+    const float k0 = ks[lane], k1 = ks[lane + 32];
+#pragma unroll
+    for (int i = 0; i < MTW; ++i) {
+      if (MODE == MAGNET_DEPTH_GAUSS) {
+        const float mu = __shfl_sync(FULL, MU, i), sg = __shfl_sync(FULL, SG, i);
+        d[i] = make_float2(__fadd_rn(mu, __fmul_rn(sg, k0)), __fadd_rn(mu, __fmul_rn(sg, k1)));   // MAGNET.py:155
+      } else {
+        d[i] = make_float2(k0, k1);
+      }
+    }
+  }
+  float2 acc[MTW];
+#pragma unroll
+  for (int i = 0; i < MTW; ++i) acc[i] = make_float2(0.f, 0.f);
+
+  mbar_wait_or_trap(bar_tma, 0);                           // camera table + reference tile landed
+  uint32_t ph_tma = 1, ph_mma = 0;
+  int it = 0;
+  const float xmax = (float)W + 1.0f, ymax = (float)H + 1.0f;
+  const float kappa = p.kappa;
+  const uint32_t g_row0 = sbase + MOFF_R, m_base = sbase + MOFF_META;
+
+  for (int v = 0; v < V; ++v) {
+    const magnet_camera* cam = cams_s + v;                 // V <= MMAXV is checked on the host
+    if (cam->valid != 1.0f) continue;                      // CTA-uniform
+    const float a0 = cam->a[0], a1 = cam->a[1], a2 = cam->a[2];
+    // (K R) ray of the pixel this lane holds (lane & 7); the pixel loop below broadcasts it
+    const float Q0 = __fmaf_rn(cam->A[2], R2, __fmaf_rn(cam->A[1], R1, __fmul_rn(cam->A[0], R0)));
+    const float Q1 = __fmaf_rn(cam->A[5], R2, __fmaf_rn(cam->A[4], R1, __fmul_rn(cam->A[3], R0)));
+    const float Q2 = __fmaf_rn(cam->A[8], R2, __fmaf_rn(cam->A[7], R1, __fmul_rn(cam->A[6], R0)));
+    const int vb = v * p.B + b;
+
+    // ---------------- projection of every hypothesis, bounding box of the tile's sample positions -------------
+    float2 cix[MTW], ciy[MTW];
+    float xl = 1e9f, xh = -1e9f, yl = 1e9f, yh = -1e9f;
+#pragma unroll
+    for (int i = 0; i < MTW; ++i) {
+      const float q0 = __shfl_sync(FULL, Q0, i), q1 = __shfl_sync(FULL, Q1, i), q2 = __shfl_sync(FULL, Q2, i);
+      float2 ix, iy, z;
+      project2(d[i], a0, a1, a2, q0, q1, q2, ix, iy, z);
+      // anything left of -1 / right of W (above / below likewise) has all four taps out of the image: clamp so that
+      // cells stay near the image and NaN (fmaxf drops it) maps to "out of bounds"
+      ix.x = fminf(fmaxf(ix.x, -2.0f), xmax); ix.y = fminf(fmaxf(ix.y, -2.0f), xmax);
+      iy.x = fminf(fmaxf(iy.x, -2.0f), ymax); iy.y = fminf(fmaxf(iy.y, -2.0f), ymax);
+      cix[i] = ix;
+      ciy[i] = iy;
+      if ((livemask >> i) & 1u) {                          // warp-uniform
+        if (act0) { xl = fminf(xl, ix.x); xh = fmaxf(xh, ix.x); yl = fminf(yl, iy.x); yh = fmaxf(yh, iy.x); }
+        if (act1) { xl = fminf(xl, ix.y); xh = fmaxf(xh, ix.y); yl = fminf(yl, iy.y); yh = fmaxf(yh, iy.y); }
+      }
+    }
+    int* bb = bbox + (it & 1) * 4;
+    {
+      const int r0 = __reduce_min_sync(FULL, (int)floorf(xl)), r1 = __reduce_max_sync(FULL, (int)floorf(xh));
+      const int r2 = __reduce_min_sync(FULL, (int)floorf(yl)), r3 = __reduce_max_sync(FULL, (int)floorf(yh));
+      if (lane == 0) { atomicMin(bb + 0, r0); atomicMax(bb + 1, r1); atomicMin(bb + 2, r2); atomicMax(bb + 3, r3); }
+    }
+    fence_proxy_async();
+    __syncthreads();                                       // box complete; region R is free (phase C of the last pass)
+    const int wx0 = bb[0], wx1 = bb[1], wy0 = bb[2], wy1 = bb[3];
+    if (tid < 4) bbox[((it + 1) & 1) * 4 + tid] = (tid & 1) ? -(1 << 28) : (1 << 28);   // re-arm the other slot
+    ++it;
+    // The cell origins span [wx0, wx1] x [wy0, wy1].  One pass when the window (origins + right / lower taps, cut into
+    // 8-cell segments) fits MSEG segments, else sub-windows of <= MSEG segments that overlap by one cell column / row;
+    // a hypothesis is evaluated in the sub-window that holds its cell origin.
+    const int nseg_all = (wx1 - wx0 + 2 + 7) >> 3, rows_all = wy1 - wy0 + 2;
+    const int nsw = min(nseg_all, 16);
+    const int rmax = nseg_all * rows_all <= MSEG ? rows_all : max(2, MSEG / nsw);
+    const int stepx = 8 * nsw - 1, stepy = rmax - 1;
+
+    for (int sy = wy0; sy <= wy1; sy += stepy) {
+      const int rows = min(stepy, wy1 - sy + 1) + 1;
+      for (int sx = wx0; sx <= wx1; sx += stepx) {
+        const int nseg = (min(stepx, wx1 - sx + 1) + 1 + 7) >> 3;
+        const int nsegs = nseg * rows;                     // <= MSEG
+        // ---------------- window + (mu, sigma) table by TMA ---------------------------------------------------
+        if (tid == 0) mbar_arrive_expect_tx(bar_tma, (uint32_t)nsegs * (SEG_BYTES + (CW ? META_SEG_BYTES : 0)));
+        if (lane == 0) {
+          for (int s = warp; s < nsegs; s += MNT / 32) {
+            const int r = s / nseg, xb = s - r * nseg;
+            tma_load_5d(sbase + MOFF_R + (uint32_t)s * SEG_BYTES, &tm_src, bar_tma, 0, sx + 8 * xb, sy + r, 0, vb);
+            if (CW) tma_load_4d(m_base + (uint32_t)s * META_SEG_BYTES, &tm_meta, bar_tma, 0, sx + 8 * xb, sy + r, vb);
+          }
+        }
+        __syncwarp();
+        const int npad = (nsegs * 8 + 15) & ~15;           // accumulator columns (N % 16 == 0)
+        const int gp = (((npad + 27) >> 5) << 5) + 4;      // row pitch of G in floats: % 32 == 4 (conflict-free stores)
+        mbar_wait_or_trap(bar_tma, ph_tma);                // every thread observes the copies (it reads the table)
+        ph_tma ^= 1u;
+        // ---------------- G = ref x window^T: 3 products x 4 K steps, one thread -------------------------------
+        if (warp == 0) {
+          tmem_fence_after_sync();
+          if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(128, (uint32_t)npad);
+            const uint64_t a_hi = umma_desc_sw128(sbase + MOFF_A, 1024), a_lo = umma_desc_sw128(sbase + MOFF_A + 8192, 1024);
+            const uint64_t b_hi = umma_desc_sw128(sbase + MOFF_R, SEG_BYTES), b_lo = umma_desc_sw128(sbase + MOFF_R + 1024, SEG_BYTES);
+            uint32_t accum = 0;
+#pragma unroll
+            for (int pr = 0; pr < 3; ++pr) {                // small cross terms first
+              const uint64_t ad = pr == 0 ? a_lo : a_hi, bd = pr == 1 ? b_lo : b_hi;
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                umma_f16(tmem_base, ad + 2u * kk, bd + 2u * kk, idesc, accum);
+                accum = 1;
+              }
+            }
+            umma_commit(bar_mma);
+          }
+          __syncwarp();
+        }
+        mbar_wait_or_trap(bar_mma, ph_mma);
+        ph_mma ^= 1u;
+        tmem_fence_after_sync();
+        // ---------------- accumulator rows 0..63 -> shared memory (over the window) ---------------------------
+        if ((warp & 3) < 2) {
+          const int row = (warp & 3) * 32 + lane;
+          float4* grow = reinterpret_cast<float4*>(regR + (size_t)row * gp);
+          for (int cc = warp >> 2; cc * 16 < npad; cc += 2) {
+            float t[16];
+            tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cc * 16), t);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) grow[cc * 4 + e] = make_float4(t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
+          }
+        }
+        tmem_fence_before_sync();
+        __syncthreads();
+#ifdef MAGNET_MMA_DEBUG
+        if (dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && it == 1 && sy == wy0 && sx == wx0) {
+          if (tid == 0) {
+            dbg[0] = (float)sx; dbg[1] = (float)sy; dbg[2] = (float)nseg; dbg[3] = (float)rows; dbg[4] = (float)npad;
+            dbg[5] = (float)gp; dbg[6] = (float)v; dbg[7] = 3.0f; dbg[8] = hdr_ref->scale; dbg[9] = hdr_src->scale;
+          }
+          for (int idx = tid; idx < MPX * npad; idx += MNT) dbg[16 + (idx / npad) * 256 + idx % npad] = regR[(idx / npad) * gp + idx % npad];
+        }
+#endif
+        // ---------------- per hypothesis: 4 G reads, 4 table reads, 3 bilinear interpolations -------------------
+        // byte offset of cell (x0, y0) in a G row = 4 * ((y0 - sy) * pitch + (x0 - sx)), evaluated in fp32 (small
+        // integers, exact) on top of 1.5 * 2^23 so that the integer sits in the mantissa
+        const float MAGIC = 12582912.0f;
+        const float sxf = (float)sx, syf = (float)sy;
+        const float xend = sx + stepx > wx1 ? 1e9f : (float)(sx + stepx), yend = sy + stepy > wy1 ? 1e9f : (float)(sy + stepy);
+        const float pitch4f = (float)(nseg * 32);
+        const uint32_t pitch4 = (uint32_t)nseg * 32u;
+        uint32_t rowaddr = g_row0 + (uint32_t)(warp * 8 * gp) * 4u;
+#pragma unroll
+        for (int i = 0; i < MTW; ++i, rowaddr += (uint32_t)gp * 4u) {
+          if (!((livemask >> i) & 1u)) continue;           // warp-uniform
+          const float2 x = cix[i], y = ciy[i];
+          const float x0a = floorf(x.x), x0b = floorf(x.y), y0a = floorf(y.x), y0b = floorf(y.y);
+          const bool pa = act0 && x0a >= sxf && x0a < xend && y0a >= syf && y0a < yend;
+          const bool pb = act1 && x0b >= sxf && x0b < xend && y0b >= syf && y0b < yend;
+          const float oa = __fmaf_rn(x0a - sxf, 4.0f, __fmaf_rn(y0a - syf, pitch4f, MAGIC));
+          const float ob = __fmaf_rn(x0b - sxf, 4.0f, __fmaf_rn(y0b - syf, pitch4f, MAGIC));
+          const uint32_t ca = pa ? (__float_as_uint(oa) & 0x3fffffu) : 0u;   // idle lanes read cell 0
+          const uint32_t cb = pb ? (__float_as_uint(ob) & 0x3fffffu) : 0u;
+          const uint32_t ga = rowaddr + ca, gb = rowaddr + cb;
+          const float ga00 = lds_f32(ga), ga01 = lds_f32(ga + 4), ga10 = lds_f32(ga + pitch4), ga11 = lds_f32(ga + pitch4 + 4);
+          const float gb00 = lds_f32(gb), gb01 = lds_f32(gb + 4), gb10 = lds_f32(gb + pitch4), gb11 = lds_f32(gb + pitch4 + 4);
+          const float fxa = x.x - x0a, fxb = x.y - x0b, fya = y.x - y0a, fyb = y.y - y0b;
+          const float costa = lerp2d(ga00, ga01, ga10, ga11, fxa, fya), costb = lerp2d(gb00, gb01, gb10, gb11, fxb, fyb);
+          bool oka, okb;
+          if (CW) {
+            const uint32_t ma = m_base + ca * 4u, mb = m_base + cb * 4u;
+            const float2 msa = lerp2d_x2(lds_f32x2(ma), lds_f32x2(ma + 16), lds_f32x2(ma + pitch4 * 4u), lds_f32x2(ma + pitch4 * 4u + 16), fxa, fya);
+            const float2 msb = lerp2d_x2(lds_f32x2(mb), lds_f32x2(mb + 16), lds_f32x2(mb + pitch4 * 4u), lds_f32x2(mb + pitch4 * 4u + 16), fxb, fyb);
+            const float q2 = __shfl_sync(FULL, Q2, i);
+            const float2 z = __fadd2_rn(make_float2(a2, a2), __fmul2_rn(make_float2(q2, q2), d[i]));
+            // homography.py:157-158: |z - mu~| < sigma~ * kappa, strict
+            oka = fabsf(__fsub_rn(z.x, msa.x)) < __fmul_rn(msa.y, kappa);
+            okb = fabsf(__fsub_rn(z.y, msb.x)) < __fmul_rn(msb.y, kappa);
+          } else {
+            oka = fabsf(costa) < 3.0e38f;
+            okb = fabsf(costb) < 3.0e38f;
+          }
+          acc[i].x += (pa && oka) ? costa : 0.0f;
+          acc[i].y += (pb && okb) ? costb : 0.0f;
+        }
+        fence_proxy_async();
+        tmem_fence_before_sync();
+        __syncthreads();                                   // G / table dead: the next copies and MMAs may overwrite
+      }
+    }
+  }
+
+  // -------- epilogue: undo the split scales, 1/V mean over ALL views (homography.py:120), coalesced store --------
+  {
+    const float inv = hdr_ref->inv_scale * hdr_src->inv_scale;   // powers of two: exact
+#pragma unroll
+    for (int i = 0; i < MTW; ++i) {
+      regR[lane * 65 + warp * 8 + i] = acc[i].x * inv;
+      regR[(lane + 32) * 65 + warp * 8 + i] = acc[i].y * inv;
+    }
+    __syncthreads();
+    const bool exact = p.inv_v_exact != 0.0f;              // V a power of two: the division is an exact scaling
+    for (int idx = tid; idx < MCH * MPX; idx += MNT) {
+      const int j = idx >> 6, pp = idx & 63;
+      const int y = ty0 + (pp >> 3), x = tx0 + (pp & 7);
+      if (j < Dc && x < W && y < H) {
+        const float a = regR[j * 65 + pp];
+        p.out[((size_t)b * D + jc + j) * HW + (size_t)y * W + x] = exact ? a * p.inv_v_exact : __fdiv_rn(a, p.vf);
+      }
+    }
+  }
+  tmem_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, M_TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// MAGNET_SRC_SPLIT16 producer: (N, 64, H, W) fp32 [+ (N, 2, H, W) Gaussians] ->
+//   header | fp16 planes (N, 2, H, W, 64): hi = fp16(x*s), lo = fp16(x*s - hi) | table (N, H, W, 4) = (mu, sigma, 0, 0)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) absmax_kernel(const float4* __restrict__ x, size_t n4, const float* __restrict__ tail,
+                                                     int ntail, unsigned* __restrict__ out) {
+  unsigned m = 0u;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x + i);
+    m = max(max(m, __float_as_uint(v.x) & 0x7fffffffu), __float_as_uint(v.y) & 0x7fffffffu);
+    m = max(max(m, __float_as_uint(v.z) & 0x7fffffffu), __float_as_uint(v.w) & 0x7fffffffu);
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) m = max(m, __float_as_uint(tail[threadIdx.x]) & 0x7fffffffu);
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m != 0u) atomicMax(out, m);
+}
+
+// power-of-two scale that maps absmax into [2^14, 2^15); 1 for an all-zero or non-finite tensor
+__device__ __forceinline__ int split16_shift(unsigned absmax_bits) {
+  const int e = (int)(absmax_bits >> 23) & 0xff;
+  if (e == 0 || e == 255) return 0;
+  return max(-100, min(100, 14 - (e - 127)));
+}
+
+__global__ void __launch_bounds__(256) split16_repack_kernel(const float* __restrict__ src, const float* __restrict__ gmm,
+                                                             unsigned char* __restrict__ dst, int N, int HW) {
+  constexpr int C = 64;
+  __shared__ float t[32 * (C + 1)];
+  Split16Header* hdr = reinterpret_cast<Split16Header*>(dst);
+  const int sh = split16_shift(hdr->absmax);
+  const float s = __uint_as_float((unsigned)(127 + sh) << 23);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    hdr->scale = s;
+    hdr->inv_scale = __uint_as_float((unsigned)(127 - sh) << 23);
+  }
+  const int xi = threadIdx.x & 31, cy = threadIdx.x >> 5;
+  const size_t img = blockIdx.y;
+  const int p0 = blockIdx.x * 32;
+  const int pix = p0 + xi;
+  for (int c = cy; c < C; c += 8) t[xi * (C + 1) + c] = pix < HW ? src[(img * C + c) * HW + pix] : 0.0f;
+  __syncthreads();
+  __half* planes = reinterpret_cast<__half*>(dst + SPLIT16_HEADER);
+  float4* meta = reinterpret_cast<float4*>(dst + SPLIT16_HEADER + (size_t)N * HW * 256);
+  const int pl = threadIdx.x >> 3, q = threadIdx.x & 7;     // pixel of the group, 8-channel chunk
+  if (p0 + pl < HW) {
+    __align__(16) __half hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float v = t[pl * (C + 1) + q * 8 + e] * s;
+      hi[e] = __float2half_rn(v);
+      lo[e] = __float2half_rn(v - __half2float(hi[e]));
+    }
+    const size_t o = (size_t)(p0 + pl) * 64 + q * 8;
+    *reinterpret_cast<uint4*>(planes + (img * 2 + 0) * (size_t)HW * 64 + o) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(planes + (img * 2 + 1) * (size_t)HW * 64 + o) = *reinterpret_cast<const uint4*>(lo);
+  }
+  if (threadIdx.x < 32 && pix < HW) {
+    float mu = 0.0f, sg = 0.0f;
+    if (gmm != nullptr) {
+      mu = gmm[(img * 2 + 0) * HW + pix];
+      sg = gmm[(img * 2 + 1) * HW + pix];
+    }
+    meta[img * HW + pix] = make_float4(mu, sg, 0.0f, 0.0f);
+  }
+}
+
+cudaError_t launch_repack_split16(const float* src, const float* gmm, void* dst, int N, int C, int H, int W,
+                                  cudaStream_t st, int* launches) {
+  if (C != 64) return cudaErrorInvalidValue;
+  const int HW = H * W;
+  const size_t n = (size_t)N * C * HW;
+  cudaError_t e = cudaMemsetAsync(dst, 0, SPLIT16_HEADER, st);
+  if (e != cudaSuccess) return e;
+  const size_t n4 = n / 4;
+  const int blocks = (int)std::min<size_t>(148 * 8, (n4 + 255) / 256 + 1);
+  absmax_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(src), n4, src + n4 * 4, (int)(n - n4 * 4),
+                                        reinterpret_cast<unsigned*>(static_cast<unsigned char*>(dst) + offsetof(Split16Header, absmax)));
+  dim3 grid((HW + 31) / 32, N), block(256);
+  split16_repack_kernel<<<grid, block, 0, st>>>(src, gmm, static_cast<unsigned char*>(dst), N, HW);
+  *launches = 2;
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn();   // cost_tma.cu
+
+// rank-5 map over the fp16 planes: (64 channels, W, H, 2 planes, N); box = 8 pixels of one row (window segment) or an
+// 8x8 tile (reference), both planes; 128-byte swizzle = the canonical K-major UMMA layout
+static cudaError_t make_planes_map(CUtensorMap* tm, const void* planes, int N, int H, int W, int box_rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return cudaErrorNotSupported;
+  const cuuint64_t dims[5] = {64, (cuuint64_t)W, (cuuint64_t)H, 2, (cuuint64_t)N};
+  const cuuint64_t strides[4] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128, (cuuint64_t)H * W * 256};
+  const cuuint32_t box[5] = {64u, 8u, (cuuint32_t)box_rows, 2u, 1u};
+  const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(planes), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+// rank-4 map over the (mu, sigma, 0, 0) table: (4 floats, W, H, N), box = 8 pixels of one row
+static cudaError_t make_meta_map(CUtensorMap* tm, const void* meta, int N, int H, int W) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return cudaErrorNotSupported;
+  const cuuint64_t dims[4] = {4, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t strides[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+  const cuuint32_t box[4] = {4u, 8u, 1u, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(meta), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+#ifdef MAGNET_MMA_DEBUG
+static float* g_mma_dbg = nullptr;
+void mma_set_debug_buffer(float* p) { g_mma_dbg = p; }
+#endif
+
+template <int MODE, bool CW>
+static cudaError_t launch_mma_mw(const CostParams& p, cudaStream_t st) {
+  static std::once_flag flags[64];
+  auto kern = cost_mma_kernel<MODE, CW>;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  cudaError_t res = cudaSuccess;
+  std::call_once(flags[dev & 63], [&] {
+    res = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, M_SMEM_TOTAL);
+    if (res == cudaSuccess)
+      res = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  });
+  if (res != cudaSuccess) return res;
+  const int N = p.B * p.V;
+  const unsigned char* refbuf = reinterpret_cast<const unsigned char*>(p.ref_feat);
+  const unsigned char* srcbuf = reinterpret_cast<const unsigned char*>(p.src_feat);
+  CUtensorMap tm_ref, tm_src, tm_meta;
+  if ((e = make_planes_map(&tm_ref, refbuf + SPLIT16_HEADER, p.B, p.H, p.W, 8)) != cudaSuccess) return e;
+  if ((e = make_planes_map(&tm_src, srcbuf + SPLIT16_HEADER, N, p.H, p.W, 1)) != cudaSuccess) return e;
+  if ((e = make_meta_map(&tm_meta, srcbuf + SPLIT16_HEADER + (size_t)N * p.HW * 256, N, p.H, p.W)) != cudaSuccess) return e;
+  const int nchunks = (p.D + MCH - 1) / MCH;
+  const int tiles = ((p.W + MTW - 1) / MTW) * ((p.H + MTH - 1) / MTH);
+  dim3 grid(tiles * nchunks, p.B), block(MNT);
+  float* dbg = nullptr;
+#ifdef MAGNET_MMA_DEBUG
+  dbg = g_mma_dbg;
+#endif
+  kern<<<grid, block, M_SMEM_TOTAL, st>>>(p, tm_ref, tm_src, tm_meta, nchunks, dbg);
+  return cudaGetLastError();
+}
+
+bool mma_supports(int C, int D, int V, int layout) {
+  return C == 64 && layout == MAGNET_SRC_SPLIT16 && D >= 1 && V <= MMAXV;
+}
+
+void mma_launch_info(int B, int H, int W, int D, int* grid, int* block, int* smem) {
+  *grid = ((W + MTW - 1) / MTW) * ((H + MTH - 1) / MTH) * ((D + MCH - 1) / MCH) * B;
+  *block = MNT;
+  *smem = M_SMEM_TOTAL;
+}
+
+size_t split16_buffer_bytes(int N, int H, int W) { return split16_bytes((size_t)N, (size_t)H * W); }
+
+cudaError_t launch_cost_mma(const CostParams& p, int mode, bool cw, cudaStream_t st) {
+  if (cw) {
+    if (mode == MAGNET_DEPTH_VOLUME) return launch_mma_mw<MAGNET_DEPTH_VOLUME, true>(p, st);
+    if (mode == MAGNET_DEPTH_GAUSS) return launch_mma_mw<MAGNET_DEPTH_GAUSS, true>(p, st);
+    return launch_mma_mw<MAGNET_DEPTH_PLANES, true>(p, st);
+  }
+  if (mode == MAGNET_DEPTH_VOLUME) return launch_mma_mw<MAGNET_DEPTH_VOLUME, false>(p, st);
+  if (mode == MAGNET_DEPTH_GAUSS) return launch_mma_mw<MAGNET_DEPTH_GAUSS, false>(p, st);
+  return launch_mma_mw<MAGNET_DEPTH_PLANES, false>(p, st);
+}
+
+}  // namespace magnet

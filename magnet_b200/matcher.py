@@ -71,6 +71,7 @@ class MatchingPlan:
         self.cams = ops.pack_cameras(intM, R, t, is_valid.to(dev, torch.int32))
         self._nghbr_feat = nghbr_feat.detach()
         self._packed = {}
+        self._ref_split = None
         # Sampler-fused loop: the global-gather kernel (TILED32) is the faster one at every measured size (profiles/
         # r2_kernels.md); pass src_layout=SRC_PIXC / variant=VARIANT_TMA for the TMA-staged kernel.
         if src_layout == _lib.SRC_PIXC and not (self.C in (16, 32, 64) and self.V <= 16):
@@ -85,6 +86,9 @@ class MatchingPlan:
         if layout not in self._packed:
             if layout == _lib.SRC_PIXC:
                 self._packed[layout] = ops.repack_pixc(self._nghbr_feat, self.src_gmm)
+            elif layout == _lib.SRC_SPLIT16:
+                self._packed[layout] = ops.repack_split16(self._nghbr_feat, self.src_gmm)
+                self._ref_split = ops.repack_split16(self.ref_feat)
             elif layout == _lib.SRC_TILED32:
                 self._packed[layout] = ops.repack_tiled32(self._nghbr_feat)
             else:
@@ -96,11 +100,15 @@ class MatchingPlan:
         layout = self.layout
         if variant == _lib.VARIANT_TMA:
             layout = _lib.SRC_PIXC                         # the TMA-staged kernel fetches its windows from PIXC
-        elif layout == _lib.SRC_PIXC and variant in (_lib.VARIANT_DIRECT, _lib.VARIANT_CELLS, _lib.VARIANT_CELLS_NOREUSE):
+        elif variant == _lib.VARIANT_MMA:
+            layout = _lib.SRC_SPLIT16                      # the tensor-core kernel reads the fp16 hi/lo planes
+        elif layout in (_lib.SRC_PIXC, _lib.SRC_SPLIT16) and variant in (_lib.VARIANT_DIRECT, _lib.VARIANT_CELLS, _lib.VARIANT_CELLS_NOREUSE):
             layout = _lib.SRC_TILED32                      # the global-gather kernels read TILED32
-        return ops.cost_volume(self.ref_feat, self._source(layout), self.rays, self.cams, V=self.V, src_layout=layout,
+        src = self._source(layout)
+        return ops.cost_volume(self.ref_feat, src, self.rays, self.cams, V=self.V, src_layout=layout,
                                consistency=True, src_gmm=self.src_gmm, kappa=self.kappa, ref_gmm=gmm.detach(),
-                               k=k, out=out, variant=variant)
+                               k=k, out=out, variant=variant,
+                               ref_split=self._ref_split if layout == _lib.SRC_SPLIT16 else None)
 
 
 def matching_loop(plan: MatchingPlan, ref_gmms: torch.Tensor, x_d3: torch.Tensor,

@@ -112,6 +112,29 @@ def repack_pixc(x: torch.Tensor, gmm: Optional[torch.Tensor] = None, out: Option
     return out
 
 
+def repack_split16(x: torch.Tensor, gmm: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(N,64,H,W) features [+ (N,2,H,W) Gaussians] -> SPLIT16 buffer (uint8): header with the power-of-two scale s, fp16
+    planes (N,2,H,W,64) with x*s = hi + lo, table (N,H,W,4) = (mu, sigma, 0, 0) — what the tensor-core kernel's TMA boxes
+    fetch (reference features: gmm=None)."""
+    x = _need_cuda_f32("x", x)
+    N, Cc, H, W = x.shape
+    gptr = None
+    if gmm is not None:
+        gmm = _need_cuda_f32("gmm", gmm)
+        if tuple(gmm.shape) != (N, 2, H, W):
+            raise _lib.MagnetError(f"gmm must be (N,2,H,W) = {(N, 2, H, W)}, got {tuple(gmm.shape)}")
+        gptr = gmm.data_ptr()
+    nbytes = int(lib().magnet_split16_bytes(N, H, W))
+    if out is None:
+        out = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    elif out.numel() * out.element_size() < nbytes or out.device != x.device:
+        raise _lib.MagnetError(f"out must hold {nbytes} bytes on {x.device}")
+    with torch.cuda.device(x.device):
+        check(lib().magnet_repack_split16_f32(x.data_ptr(), gptr, out.data_ptr(), N, Cc, H, W, _stream(x.device)),
+              "magnet_repack_split16_f32")
+    return out
+
+
 def sample_depths(gmm: torch.Tensor, k, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Sampler alone (MAGNET.py:154-156): gmm (B,2,H,W) -> d_volume (B,D,H,W)."""
     gmm = _need_cuda_f32("gmm", gmm)
@@ -130,11 +153,18 @@ def cost_volume(ref_feat: torch.Tensor, src_feat: torch.Tensor, rays: torch.Tens
                 V: int, src_layout: int, consistency: bool, src_gmm: Optional[torch.Tensor] = None,
                 kappa: float = 5.0, d_volume: Optional[torch.Tensor] = None,
                 ref_gmm: Optional[torch.Tensor] = None, k=None, planes: bool = False, softmax: bool = False,
-                variant: int = _lib.VARIANT_AUTO, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                variant: int = _lib.VARIANT_AUTO, out: Optional[torch.Tensor] = None,
+                ref_split: Optional[torch.Tensor] = None) -> torch.Tensor:
     """One launch of magnet_cost_volume_f32.  Depth source: ``d_volume`` (drop-in), or ``ref_gmm`` + ``k``
-    (fused sampler), or ``k`` with ``planes=True`` (fronto-parallel planes)."""
+    (fused sampler), or ``k`` with ``planes=True`` (fronto-parallel planes).  With ``src_layout=SRC_SPLIT16`` both
+    ``src_feat`` and ``ref_split`` are ``repack_split16`` buffers (``ref_feat`` then only supplies the shape)."""
     ref_feat = _need_cuda_f32("ref_feat", ref_feat)
-    src_feat = _need_cuda_f32("src_feat", src_feat)
+    if src_layout == _lib.SRC_SPLIT16:
+        for nm, buf in (("src_feat", src_feat), ("ref_split", ref_split)):
+            if not (isinstance(buf, torch.Tensor) and buf.is_cuda and buf.dtype == torch.uint8 and buf.is_contiguous()):
+                raise _lib.MagnetError(f"{nm} must be a contiguous uint8 CUDA buffer from repack_split16")
+    else:
+        src_feat = _need_cuda_f32("src_feat", src_feat)
     rays = _need_cuda_f32("rays", rays)
     cams = _need_cuda_f32("cams", cams)
     if ref_feat.dim() != 4:
@@ -144,15 +174,19 @@ def cost_volume(ref_feat: torch.Tensor, src_feat: torch.Tensor, rays: torch.Tens
         raise _lib.MagnetError(f"V must be positive, got {V}")
     # every operand against (B, V, D, C, H, W): a mismatch would read out of bounds, the reference raises instead
     src_shape = {_lib.SRC_NCHW: (V * B, Cc, H, W), _lib.SRC_TILED32: (V * B, H, (W + 31) // 32, Cc // 4, 32, 4),
-                 _lib.SRC_PIXC: (V * B, H, W, Cc + 4)}.get(src_layout)
+                 _lib.SRC_PIXC: (V * B, H, W, Cc + 4),
+                 _lib.SRC_SPLIT16: (int(lib().magnet_split16_bytes(V * B, H, W)),)}.get(src_layout)
     if src_shape is None:
         raise _lib.MagnetError(f"unknown src_layout {src_layout}")
     _expect("src_feat", src_feat, src_shape)
+    if src_layout == _lib.SRC_SPLIT16:
+        _expect("ref_split", ref_split, (int(lib().magnet_split16_bytes(B, H, W)),))
     _expect("rays", rays, (B, 3, H * W))
     if cams.numel() != B * V * 16:
         raise _lib.MagnetError(f"cams must hold B*V = {B * V} camera records of 16 floats, got {tuple(cams.shape)}")
     dev = _same_device(("ref_feat", ref_feat), ("src_feat", src_feat), ("rays", rays), ("cams", cams),
-                       ("src_gmm", src_gmm), ("d_volume", d_volume), ("ref_gmm", ref_gmm), ("out", out))
+                       ("src_gmm", src_gmm), ("d_volume", d_volume), ("ref_gmm", ref_gmm), ("out", out),
+                       ("ref_split", ref_split))
     a = CostArgs()
     a.B, a.V, a.C, a.H, a.W = B, V, Cc, H, W
     a.src_layout = src_layout
@@ -162,7 +196,10 @@ def cost_volume(ref_feat: torch.Tensor, src_feat: torch.Tensor, rays: torch.Tens
     a.kappa = float(kappa)
     a.ref_feat, a.src_feat, a.rays, a.cams = ref_feat.data_ptr(), src_feat.data_ptr(), rays.data_ptr(), cams.data_ptr()
     keep = [ref_feat, src_feat, rays, cams]
-    if consistency and src_layout != _lib.SRC_PIXC:          # PIXC carries the source Gaussians inside src_feat
+    if src_layout == _lib.SRC_SPLIT16:
+        a.ref_feat = ref_split.data_ptr()
+        keep.append(ref_split)
+    if consistency and src_layout not in (_lib.SRC_PIXC, _lib.SRC_SPLIT16):   # those carry the source Gaussians inside src_feat
         src_gmm = _need_cuda_f32("src_gmm", src_gmm)
         _expect("src_gmm", src_gmm, (V * B, 2, H, W))
         a.src_gmm = src_gmm.data_ptr()
@@ -236,7 +273,7 @@ def cost_launch_info(B, V, D, Cc, H, W, variant=_lib.VARIANT_AUTO):
     """(grid CTAs, threads per CTA, dynamic smem bytes) the cost kernel would use for these sizes."""
     a = CostArgs()
     a.B, a.V, a.D, a.C, a.H, a.W = B, V, D, Cc, H, W
-    layout = _lib.SRC_PIXC if variant == _lib.VARIANT_TMA else _lib.SRC_TILED32
+    layout = {_lib.VARIANT_TMA: _lib.SRC_PIXC, _lib.VARIANT_MMA: _lib.SRC_SPLIT16}.get(variant, _lib.SRC_TILED32)
     a.depth_mode, a.src_layout, a.consistency, a.variant = _lib.DEPTH_PLANES, layout, 0, variant
     one = C.c_void_p(0x1000)                       # never dereferenced: validated for non-NULL / alignment only
     a.ref_feat = a.src_feat = a.rays = a.cams = a.out = a.k_host = one

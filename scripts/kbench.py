@@ -7,7 +7,7 @@ import magnet_b200
 from magnet_b200 import _lib, ops
 from magnet_b200.synthetic import make_config
 cfg = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
-variant = {"auto": 0, "direct": 1, "cells": 2, "noreuse": 3, "tma": 4}[(sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] else "auto")]
+variant = {"auto": 0, "direct": 1, "cells": 2, "noreuse": 3, "tma": 4, "mma": 5}[(sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] else "auto")]
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 30
 mode = sys.argv[4] if len(sys.argv) > 4 else "gauss"
 inp = make_config(cfg, seed=1)
@@ -23,9 +23,11 @@ def launch():
     if dvol is None:
         plan.cost(g.ref_gmms, k, out=out, variant=variant)
     else:
-        layout = _lib.SRC_PIXC if variant == 4 else _lib.SRC_TILED32
-        ops.cost_volume(plan.ref_feat, plan._source(layout), plan.rays, plan.cams, V=plan.V, src_layout=layout, consistency=True,
-                        src_gmm=plan.src_gmm, kappa=plan.kappa, d_volume=dvol, out=out, variant=variant)
+        layout = {4: _lib.SRC_PIXC, 5: _lib.SRC_SPLIT16}.get(variant, _lib.SRC_TILED32)
+        src = plan._source(layout)
+        ops.cost_volume(plan.ref_feat, src, plan.rays, plan.cams, V=plan.V, src_layout=layout, consistency=True,
+                        src_gmm=plan.src_gmm, kappa=plan.kappa, d_volume=dvol, out=out, variant=variant,
+                        ref_split=plan._ref_split if layout == _lib.SRC_SPLIT16 else None)
 
 
 for _ in range(3):

@@ -36,6 +36,7 @@
 #include <algorithm>
 #include <cstddef>
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tma_common.cuh"
@@ -60,11 +61,12 @@ constexpr int MOFF_META = MOFF_R + MR_BYTES;                // float4[256] (mu, 
 constexpr int MOFF_CAM = MOFF_META + MSEG * META_SEG_BYTES; // magnet_camera[MMAXV]
 constexpr int MOFF_KS = MOFF_CAM + MMAXV * 64;              // float[MCH]
 constexpr int MOFF_BBOX = MOFF_KS + MCH * 4;                // int[2 slots][4]
-constexpr int MOFF_BAR = MOFF_BBOX + 64;                    // 2 mbarriers, TMEM base address
-constexpr int M_SMEM_USED = MOFF_BAR + 32;
+constexpr int MOFF_BAR = MOFF_BBOX + 64;                    // 3 mbarriers, TMEM base address
+constexpr int MOFF_ACC = MOFF_BAR + 64;                     // float[MCH][65]: view accumulators, hypothesis-major
+constexpr int M_SMEM_USED = MOFF_ACC + MCH * 65 * 4;
 constexpr int M_SMEM_TOTAL = M_SMEM_USED + 1024;            // slack for the 1024-byte alignment of the base
 static_assert(MR_BYTES >= MSEG * SEG_BYTES && MR_BYTES >= MPX * 260 * 4 && MR_BYTES >= MCH * 65 * 4, "region R");
-static_assert(2 * (M_SMEM_TOTAL + 1024) <= 228 * 1024, "two CTAs per SM");
+static_assert(2 * (M_SMEM_TOTAL + 1024) <= 227 * 1024, "two CTAs per SM");
 
 // header of a MAGNET_SRC_SPLIT16 buffer (256 bytes)
 struct Split16Header {
@@ -79,10 +81,11 @@ __host__ __device__ inline size_t split16_bytes(size_t N, size_t HW) { return SP
 __device__ __forceinline__ void mbar_wait_or_trap(uint32_t bar, uint32_t parity) {
   // bounded spin: a protocol error must surface as a launch failure, not as a hung GPU
 #pragma unroll 1
-  for (int it = 0; it < (1 << 24); ++it) {
+  for (int it = 0; it < (1 << 22); ++it) {
     uint32_t done;
-    asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}"
-                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    // the suspend-time hint lets the hardware park the warp instead of spinning on issue slots the other CTA needs
+    asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\nselp.u32 %0, 1, 0, P1;\n}"
+                 : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
     if (done) return;
   }
   __trap();
@@ -126,7 +129,8 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
   float* ks = reinterpret_cast<float*>(smem + MOFF_KS);
   int* bbox = reinterpret_cast<int*>(smem + MOFF_BBOX);
   float* regR = reinterpret_cast<float*>(smem + MOFF_R);
-  const uint32_t bar_tma = sbase + MOFF_BAR, bar_mma = sbase + MOFF_BAR + 8;
+  const uint32_t bar_tma = sbase + MOFF_BAR, bar_mma = sbase + MOFF_BAR + 8, bar_cam = sbase + MOFF_BAR + 24;
+  float* acc_s = reinterpret_cast<float*>(smem + MOFF_ACC);
   const unsigned FULL = 0xffffffffu;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -137,7 +141,6 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
   const int jc = (blockIdx.x % nchunks) * MCH;
   const int Dc = min(MCH, D - jc);
   const int tx0 = (tile % tiles_x) * MTW, ty0 = (tile / tiles_x) * MTH;
-  const bool act0 = lane < Dc, act1 = lane + 32 < Dc;
 
   const unsigned char* refbuf = reinterpret_cast<const unsigned char*>(p.ref_feat);
   const unsigned char* srcbuf = reinterpret_cast<const unsigned char*>(p.src_feat);
@@ -148,19 +151,25 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
   if (tid == 0) {
     mbar_init(bar_tma, 1);
     mbar_init(bar_mma, 1);
+    mbar_init(bar_cam, 1);
     fence_mbar_init();
     prefetch_tmap(&tm_ref);
     prefetch_tmap(&tm_src);
     prefetch_tmap(&tm_meta);
   }
   if (tid < 8) bbox[tid] = (tid & 1) ? -(1 << 28) : (1 << 28);       // [slot][x_lo, x_hi, y_lo, y_hi]
-  if (tid < MCH) ks[tid] = (MODE != MAGNET_DEPTH_VOLUME && jc + tid < D) ? p.k[jc + tid] : 0.0f;
+  // lanes beyond the last hypothesis of the chunk replicate it (same sample position: inside every window, no
+  // predicates); their accumulator rows are never stored
+  if (tid < MCH) ks[tid] = MODE != MAGNET_DEPTH_VOLUME ? p.k[min(jc + tid, D - 1)] : 0.0f;
+  for (int idx = tid; idx < MCH * 65; idx += MNT) acc_s[idx] = 0.0f;
   tmem_fence_before_sync();
   __syncthreads();
   tmem_fence_after_sync();
-  if (tid == 0) {                                          // camera table of the batch element + the reference tile
-    mbar_arrive_expect_tx(bar_tma, (uint32_t)V * 64u + 16384u);
-    bulk_load(sbase + MOFF_CAM, p.cams + (size_t)b * V, (uint32_t)V * 64u, bar_tma);
+  if (tid == 0) {
+    // camera table of the batch element (own barrier, needed first) and the reference tile: its 16 KB complete on the
+    // window barrier, armed together with the first window (the transaction count may run negative until then)
+    mbar_arrive_expect_tx(bar_cam, (uint32_t)V * 64u);
+    bulk_load(sbase + MOFF_CAM, p.cams + (size_t)b * V, (uint32_t)V * 64u, bar_cam);
     tma_load_5d(sbase + MOFF_A, &tm_ref, bar_tma, 0, tx0, ty0, 0, b);
   }
   const uint32_t tmem_base = *reinterpret_cast<const volatile uint32_t*>(smem + MOFF_BAR + 16);
@@ -182,39 +191,36 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
     }
     livemask = __ballot_sync(FULL, live) & 0xffu;
   }
-  // my two hypotheses of every pixel of the row: d[i] = (hypothesis jc + lane, hypothesis jc + 32 + lane)
-  float2 d[MTW];
+  // my two hypotheses of every pixel of the row: (hypothesis jc + lane, hypothesis jc + 32 + lane).  Read from the
+  // depth volume they stay in registers; sampled (MAGNET.py:155: multiply, then add) or plane depths are recomputed
+  // from the pixel's Gaussian where needed (2 shuffles + 2 packed instructions instead of 16 registers).
+  float2 dvol[MODE == MAGNET_DEPTH_VOLUME ? MTW : 1];
+  float2 k2 = make_float2(0.f, 0.f);
   if (MODE == MAGNET_DEPTH_VOLUME) {                       // coalesced read, transposed through shared memory
     for (int idx = tid; idx < MCH * MPX; idx += MNT) {
       const int j = idx >> 6, pp = idx & 63;
       const int y = ty0 + (pp >> 3), x = tx0 + (pp & 7);
-      float v = 0.0f;
-      if (j < Dc && x < W && y < H) v = ldg_f(p.d_volume + ((size_t)b * D + jc + j) * HW + (size_t)y * W + x);
-      regR[j * 65 + pp] = v;
+      const size_t n = (size_t)min(y, H - 1) * W + min(x, W - 1);
+      regR[j * 65 + pp] = ldg_f(p.d_volume + ((size_t)b * D + jc + min(j, Dc - 1)) * HW + n);
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < MTW; ++i) d[i] = make_float2(regR[lane * 65 + warp * 8 + i], regR[(lane + 32) * 65 + warp * 8 + i]);
+    for (int i = 0; i < MTW; ++i) dvol[i] = make_float2(regR[lane * 65 + warp * 8 + i], regR[(lane + 32) * 65 + warp * 8 + i]);
     fence_proxy_async();
     __syncthreads();
   } else {
-    const float k0 = ks[lane], k1 = ks[lane + 32];
-#pragma unroll
-    for (int i = 0; i < MTW; ++i) {
-      if (MODE == MAGNET_DEPTH_GAUSS) {
-        const float mu = __shfl_sync(FULL, MU, i), sg = __shfl_sync(FULL, SG, i);
-        d[i] = make_float2(__fadd_rn(mu, __fmul_rn(sg, k0)), __fadd_rn(mu, __fmul_rn(sg, k1)));   // MAGNET.py:155
-      } else {
-        d[i] = make_float2(k0, k1);
-      }
-    }
+    k2 = make_float2(ks[lane], ks[lane + 32]);
   }
-  float2 acc[MTW];
-#pragma unroll
-  for (int i = 0; i < MTW; ++i) acc[i] = make_float2(0.f, 0.f);
+  auto depth2 = [&](const int i) -> float2 {
+    if (MODE == MAGNET_DEPTH_VOLUME) return dvol[i];
+    if (MODE == MAGNET_DEPTH_PLANES) return k2;
+    const float mu = __shfl_sync(FULL, MU, i), sg = __shfl_sync(FULL, SG, i);
+    return __fadd2_rn(make_float2(mu, mu), __fmul2_rn(make_float2(sg, sg), k2));
+  };
 
-  mbar_wait_or_trap(bar_tma, 0);                           // camera table + reference tile landed
-  uint32_t ph_tma = 1, ph_mma = 0;
+  mbar_wait_or_trap(bar_cam, 0);                           // camera table landed
+  uint32_t ph_tma = 0, ph_mma = 0;
+  bool first = true;                                       // the first window also waits for the reference tile
   int it = 0;
   const float xmax = (float)W + 1.0f, ymax = (float)H + 1.0f;
   const float kappa = p.kappa;
@@ -237,7 +243,7 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
     for (int i = 0; i < MTW; ++i) {
       const float q0 = __shfl_sync(FULL, Q0, i), q1 = __shfl_sync(FULL, Q1, i), q2 = __shfl_sync(FULL, Q2, i);
       float2 ix, iy, z;
-      project2(d[i], a0, a1, a2, q0, q1, q2, ix, iy, z);
+      project2(depth2(i), a0, a1, a2, q0, q1, q2, ix, iy, z);
       // anything left of -1 / right of W (above / below likewise) has all four taps out of the image: clamp so that
       // cells stay near the image and NaN (fmaxf drops it) maps to "out of bounds"
       ix.x = fminf(fmaxf(ix.x, -2.0f), xmax); ix.y = fminf(fmaxf(ix.y, -2.0f), xmax);
@@ -245,8 +251,8 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
       cix[i] = ix;
       ciy[i] = iy;
       if ((livemask >> i) & 1u) {                          // warp-uniform
-        if (act0) { xl = fminf(xl, ix.x); xh = fmaxf(xh, ix.x); yl = fminf(yl, iy.x); yh = fmaxf(yh, iy.x); }
-        if (act1) { xl = fminf(xl, ix.y); xh = fmaxf(xh, ix.y); yl = fminf(yl, iy.y); yh = fmaxf(yh, iy.y); }
+        xl = fminf(xl, fminf(ix.x, ix.y)); xh = fmaxf(xh, fmaxf(ix.x, ix.y));
+        yl = fminf(yl, fminf(iy.x, iy.y)); yh = fmaxf(yh, fmaxf(iy.x, iy.y));
       }
     }
     int* bb = bbox + (it & 1) * 4;
@@ -274,7 +280,9 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
         const int nseg = (min(stepx, wx1 - sx + 1) + 1 + 7) >> 3;
         const int nsegs = nseg * rows;                     // <= MSEG
         // ---------------- window + (mu, sigma) table by TMA ---------------------------------------------------
-        if (tid == 0) mbar_arrive_expect_tx(bar_tma, (uint32_t)nsegs * (SEG_BYTES + (CW ? META_SEG_BYTES : 0)));
+        if (tid == 0)
+          mbar_arrive_expect_tx(bar_tma, (uint32_t)nsegs * (SEG_BYTES + (CW ? META_SEG_BYTES : 0)) + (first ? 16384u : 0u));
+        first = false;
         if (lane == 0) {
           for (int s = warp; s < nsegs; s += MNT / 32) {
             const int r = s / nseg, xb = s - r * nseg;
@@ -336,45 +344,57 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
         // ---------------- per hypothesis: 4 G reads, 4 table reads, 3 bilinear interpolations -------------------
         // byte offset of cell (x0, y0) in a G row = 4 * ((y0 - sy) * pitch + (x0 - sx)), evaluated in fp32 (small
         // integers, exact) on top of 1.5 * 2^23 so that the integer sits in the mantissa
-        const float MAGIC = 12582912.0f;
-        const float sxf = (float)sx, syf = (float)sy;
-        const float xend = sx + stepx > wx1 ? 1e9f : (float)(sx + stepx), yend = sy + stepy > wy1 ? 1e9f : (float)(sy + stepy);
-        const float pitch4f = (float)(nseg * 32);
-        const uint32_t pitch4 = (uint32_t)nseg * 32u;
-        uint32_t rowaddr = g_row0 + (uint32_t)(warp * 8 * gp) * 4u;
+        const bool single = nseg_all * rows_all <= MSEG;    // every cell origin lies in this (only) window
+        auto phase_c = [&](auto single_tag) {
+          constexpr bool SINGLE = decltype(single_tag)::value;
+          const float MAGIC = 12582912.0f;
+          const float sxf = (float)sx, syf = (float)sy;
+          const float xend = sx + stepx > wx1 ? 1e9f : (float)(sx + stepx), yend = sy + stepy > wy1 ? 1e9f : (float)(sy + stepy);
+          const float pitch4f = (float)(nseg * 32);
+          const uint32_t pitch4 = (uint32_t)nseg * 32u;
+          uint32_t rowaddr = g_row0 + (uint32_t)(warp * 8 * gp) * 4u;
+          float* accp = acc_s + lane * 65 + warp * 8;
 #pragma unroll
-        for (int i = 0; i < MTW; ++i, rowaddr += (uint32_t)gp * 4u) {
-          if (!((livemask >> i) & 1u)) continue;           // warp-uniform
-          const float2 x = cix[i], y = ciy[i];
-          const float x0a = floorf(x.x), x0b = floorf(x.y), y0a = floorf(y.x), y0b = floorf(y.y);
-          const bool pa = act0 && x0a >= sxf && x0a < xend && y0a >= syf && y0a < yend;
-          const bool pb = act1 && x0b >= sxf && x0b < xend && y0b >= syf && y0b < yend;
-          const float oa = __fmaf_rn(x0a - sxf, 4.0f, __fmaf_rn(y0a - syf, pitch4f, MAGIC));
-          const float ob = __fmaf_rn(x0b - sxf, 4.0f, __fmaf_rn(y0b - syf, pitch4f, MAGIC));
-          const uint32_t ca = pa ? (__float_as_uint(oa) & 0x3fffffu) : 0u;   // idle lanes read cell 0
-          const uint32_t cb = pb ? (__float_as_uint(ob) & 0x3fffffu) : 0u;
-          const uint32_t ga = rowaddr + ca, gb = rowaddr + cb;
-          const float ga00 = lds_f32(ga), ga01 = lds_f32(ga + 4), ga10 = lds_f32(ga + pitch4), ga11 = lds_f32(ga + pitch4 + 4);
-          const float gb00 = lds_f32(gb), gb01 = lds_f32(gb + 4), gb10 = lds_f32(gb + pitch4), gb11 = lds_f32(gb + pitch4 + 4);
-          const float fxa = x.x - x0a, fxb = x.y - x0b, fya = y.x - y0a, fyb = y.y - y0b;
-          const float costa = lerp2d(ga00, ga01, ga10, ga11, fxa, fya), costb = lerp2d(gb00, gb01, gb10, gb11, fxb, fyb);
-          bool oka, okb;
-          if (CW) {
-            const uint32_t ma = m_base + ca * 4u, mb = m_base + cb * 4u;
-            const float2 msa = lerp2d_x2(lds_f32x2(ma), lds_f32x2(ma + 16), lds_f32x2(ma + pitch4 * 4u), lds_f32x2(ma + pitch4 * 4u + 16), fxa, fya);
-            const float2 msb = lerp2d_x2(lds_f32x2(mb), lds_f32x2(mb + 16), lds_f32x2(mb + pitch4 * 4u), lds_f32x2(mb + pitch4 * 4u + 16), fxb, fyb);
-            const float q2 = __shfl_sync(FULL, Q2, i);
-            const float2 z = __fadd2_rn(make_float2(a2, a2), __fmul2_rn(make_float2(q2, q2), d[i]));
-            // homography.py:157-158: |z - mu~| < sigma~ * kappa, strict
-            oka = fabsf(__fsub_rn(z.x, msa.x)) < __fmul_rn(msa.y, kappa);
-            okb = fabsf(__fsub_rn(z.y, msb.x)) < __fmul_rn(msb.y, kappa);
-          } else {
-            oka = fabsf(costa) < 3.0e38f;
-            okb = fabsf(costb) < 3.0e38f;
+          for (int i = 0; i < MTW; ++i, rowaddr += (uint32_t)gp * 4u) {
+            if (!((livemask >> i) & 1u)) continue;         // warp-uniform
+            const float2 x = cix[i], y = ciy[i];
+            const float x0a = floorf(x.x), x0b = floorf(x.y), y0a = floorf(y.x), y0b = floorf(y.y);
+            const float oa = __fmaf_rn(x0a - sxf, 4.0f, __fmaf_rn(y0a - syf, pitch4f, MAGIC));
+            const float ob = __fmaf_rn(x0b - sxf, 4.0f, __fmaf_rn(y0b - syf, pitch4f, MAGIC));
+            uint32_t ca = __float_as_uint(oa) & 0x3fffffu, cb = __float_as_uint(ob) & 0x3fffffu;
+            bool pa = true, pb = true;
+            if (!SINGLE) {                                 // evaluated in the sub-window that holds the cell origin
+              pa = x0a >= sxf && x0a < xend && y0a >= syf && y0a < yend;
+              pb = x0b >= sxf && x0b < xend && y0b >= syf && y0b < yend;
+              ca = pa ? ca : 0u;                           // the others read cell 0
+              cb = pb ? cb : 0u;
+            }
+            const uint32_t ga = rowaddr + ca, gb = rowaddr + cb;
+            const float ga00 = lds_f32(ga), ga01 = lds_f32(ga + 4), ga10 = lds_f32(ga + pitch4), ga11 = lds_f32(ga + pitch4 + 4);
+            const float gb00 = lds_f32(gb), gb01 = lds_f32(gb + 4), gb10 = lds_f32(gb + pitch4), gb11 = lds_f32(gb + pitch4 + 4);
+            const float fxa = x.x - x0a, fxb = x.y - x0b, fya = y.x - y0a, fyb = y.y - y0b;
+            const float costa = lerp2d(ga00, ga01, ga10, ga11, fxa, fya), costb = lerp2d(gb00, gb01, gb10, gb11, fxb, fyb);
+            bool oka, okb;
+            if (CW) {
+              const uint32_t ma = m_base + ca * 4u, mb = m_base + cb * 4u;
+              const float2 msa = lerp2d_x2(lds_f32x2(ma), lds_f32x2(ma + 16), lds_f32x2(ma + pitch4 * 4u), lds_f32x2(ma + pitch4 * 4u + 16), fxa, fya);
+              const float2 msb = lerp2d_x2(lds_f32x2(mb), lds_f32x2(mb + 16), lds_f32x2(mb + pitch4 * 4u), lds_f32x2(mb + pitch4 * 4u + 16), fxb, fyb);
+              const float q2 = __shfl_sync(FULL, Q2, i);
+              const float2 z = __fadd2_rn(make_float2(a2, a2), __fmul2_rn(make_float2(q2, q2), depth2(i)));
+              // homography.py:157-158: |z - mu~| < sigma~ * kappa, strict
+              oka = fabsf(__fsub_rn(z.x, msa.x)) < __fmul_rn(msa.y, kappa);
+              okb = fabsf(__fsub_rn(z.y, msb.x)) < __fmul_rn(msb.y, kappa);
+            } else {
+              oka = fabsf(costa) < 3.0e38f;
+              okb = fabsf(costb) < 3.0e38f;
+            }
+            // the accumulator of (hypothesis, pixel) is touched by this lane only
+            if (pa && oka) accp[i] += costa;
+            if (pb && okb) accp[32 * 65 + i] += costb;
           }
-          acc[i].x += (pa && oka) ? costa : 0.0f;
-          acc[i].y += (pb && okb) ? costb : 0.0f;
-        }
+        };
+        if (single) phase_c(std::true_type{});
+        else phase_c(std::false_type{});
         fence_proxy_async();
         tmem_fence_before_sync();
         __syncthreads();                                   // G / table dead: the next copies and MMAs may overwrite
@@ -382,21 +402,20 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
     }
   }
 
+  if (first) {                                             // no valid view: the reference-tile copy is still in flight
+    if (tid == 0) mbar_arrive_expect_tx(bar_tma, 16384u);
+    mbar_wait_or_trap(bar_tma, ph_tma);
+  }
+
   // -------- epilogue: undo the split scales, 1/V mean over ALL views (homography.py:120), coalesced store --------
   {
     const float inv = hdr_ref->inv_scale * hdr_src->inv_scale;   // powers of two: exact
-#pragma unroll
-    for (int i = 0; i < MTW; ++i) {
-      regR[lane * 65 + warp * 8 + i] = acc[i].x * inv;
-      regR[(lane + 32) * 65 + warp * 8 + i] = acc[i].y * inv;
-    }
-    __syncthreads();
     const bool exact = p.inv_v_exact != 0.0f;              // V a power of two: the division is an exact scaling
     for (int idx = tid; idx < MCH * MPX; idx += MNT) {
       const int j = idx >> 6, pp = idx & 63;
       const int y = ty0 + (pp >> 3), x = tx0 + (pp & 7);
       if (j < Dc && x < W && y < H) {
-        const float a = regR[j * 65 + pp];
+        const float a = acc_s[j * 65 + pp] * inv;
         p.out[((size_t)b * D + jc + j) * HW + (size_t)y * W + x] = exact ? a * p.inv_v_exact : __fdiv_rn(a, p.vf);
       }
     }

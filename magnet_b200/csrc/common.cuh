@@ -60,7 +60,9 @@ __device__ __forceinline__ void project2(const float2 d, float a0, float a1, flo
                                          float2& ix, float2& iy, float2& z) {
   const float2 P0 = __ffma2_rn(make_float2(q0, q0), d, make_float2(a0, a0));
   const float2 P1 = __ffma2_rn(make_float2(q1, q1), d, make_float2(a1, a1));
-  z = __fadd2_rn(make_float2(a2, a2), __fmul2_rn(make_float2(q2, q2), d));
+  // the products are rounded by scalar __fmul_rn: a packed __fmul2_rn feeding __fadd2_rn is contracted into one FFMA2
+  // by the compiler (no FMUL2 in SASS), which would round z once instead of twice
+  z = __fadd2_rn(make_float2(a2, a2), make_float2(__fmul_rn(q2, d.x), __fmul_rn(q2, d.y)));
   const float2 zp = __fadd2_rn(z, make_float2(1e-10f, 1e-10f));
   float2 r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(zp.x));

@@ -63,7 +63,8 @@ constexpr int MOFF_KS = MOFF_CAM + MMAXV * 64;              // float[MCH]
 constexpr int MOFF_BBOX = MOFF_KS + MCH * 4;                // int[2 slots][4]
 constexpr int MOFF_BAR = MOFF_BBOX + 64;                    // 3 mbarriers, TMEM base address
 constexpr int MOFF_ACC = MOFF_BAR + 64;                     // float[MCH][65]: view accumulators, hypothesis-major
-constexpr int M_SMEM_USED = MOFF_ACC + MCH * 65 * 4;
+constexpr int MOFF_PIX = MOFF_ACC + MCH * 65 * 4;           // float4[8 warps][8 pixels][2]: (q0,q1,q2,-) (q2,mu,sigma,-)
+constexpr int M_SMEM_USED = MOFF_PIX + 8 * 8 * 32;
 constexpr int M_SMEM_TOTAL = M_SMEM_USED + 1024;            // slack for the 1024-byte alignment of the base
 static_assert(MR_BYTES >= MSEG * SEG_BYTES && MR_BYTES >= MPX * 260 * 4 && MR_BYTES >= MCH * 65 * 4, "region R");
 static_assert(2 * (M_SMEM_TOTAL + 1024) <= 227 * 1024, "two CTAs per SM");
@@ -147,16 +148,21 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
   const Split16Header* hdr_ref = reinterpret_cast<const Split16Header*>(refbuf);
   const Split16Header* hdr_src = reinterpret_cast<const Split16Header*>(srcbuf);
 
-  if (warp == 0) tmem_alloc(sbase + MOFF_BAR + 16, M_TMEM_COLS);
   if (tid == 0) {
     mbar_init(bar_tma, 1);
     mbar_init(bar_mma, 1);
     mbar_init(bar_cam, 1);
     fence_mbar_init();
-    prefetch_tmap(&tm_ref);
+    // first of all: camera table of the batch element (own barrier, needed first) and the reference tile, whose 16 KB
+    // complete on the window barrier, armed together with the first window (the transaction count may run negative
+    // until then).  Nothing else touches these regions.
+    mbar_arrive_expect_tx(bar_cam, (uint32_t)V * 64u);
+    bulk_load(sbase + MOFF_CAM, p.cams + (size_t)b * V, (uint32_t)V * 64u, bar_cam);
+    tma_load_5d(sbase + MOFF_A, &tm_ref, bar_tma, 0, tx0, ty0, 0, b);
     prefetch_tmap(&tm_src);
     prefetch_tmap(&tm_meta);
   }
+  if (warp == 1) tmem_alloc(sbase + MOFF_BAR + 32, M_TMEM_COLS);
   if (tid < 8) bbox[tid] = (tid & 1) ? -(1 << 28) : (1 << 28);       // [slot][x_lo, x_hi, y_lo, y_hi]
   // lanes beyond the last hypothesis of the chunk replicate it (same sample position: inside every window, no
   // predicates); their accumulator rows are never stored
@@ -165,14 +171,7 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
   tmem_fence_before_sync();
   __syncthreads();
   tmem_fence_after_sync();
-  if (tid == 0) {
-    // camera table of the batch element (own barrier, needed first) and the reference tile: its 16 KB complete on the
-    // window barrier, armed together with the first window (the transaction count may run negative until then)
-    mbar_arrive_expect_tx(bar_cam, (uint32_t)V * 64u);
-    bulk_load(sbase + MOFF_CAM, p.cams + (size_t)b * V, (uint32_t)V * 64u, bar_cam);
-    tma_load_5d(sbase + MOFF_A, &tm_ref, bar_tma, 0, tx0, ty0, 0, b);
-  }
-  const uint32_t tmem_base = *reinterpret_cast<const volatile uint32_t*>(smem + MOFF_BAR + 16);
+  const uint32_t tmem_base = *reinterpret_cast<const volatile uint32_t*>(smem + MOFF_BAR + 32);
 
   // ---- per-warp constants: lane i (mod 8) holds the ray / Gaussian of pixel i of my tile row ----------------
   const int py = ty0 + warp;
@@ -211,12 +210,14 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
   } else {
     k2 = make_float2(ks[lane], ks[lane + 32]);
   }
-  auto depth2 = [&](const int i) -> float2 {
+  // (mu, sigma) come from the warp's pixel table; the product is rounded by scalar __fmul_rn (a packed multiply feeding
+  // a packed add would be contracted into one FFMA2)
+  auto depth2 = [&](const int i, const float mu, const float sg) -> float2 {
     if (MODE == MAGNET_DEPTH_VOLUME) return dvol[i];
     if (MODE == MAGNET_DEPTH_PLANES) return k2;
-    const float mu = __shfl_sync(FULL, MU, i), sg = __shfl_sync(FULL, SG, i);
-    return __fadd2_rn(make_float2(mu, mu), __fmul2_rn(make_float2(sg, sg), k2));
+    return __fadd2_rn(make_float2(mu, mu), make_float2(__fmul_rn(sg, k2.x), __fmul_rn(sg, k2.y)));
   };
+  float4* pixt = reinterpret_cast<float4*>(smem + MOFF_PIX) + warp * 16;
 
   mbar_wait_or_trap(bar_cam, 0);                           // camera table landed
   uint32_t ph_tma = 0, ph_mma = 0;
@@ -234,6 +235,12 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
     const float Q0 = __fmaf_rn(cam->A[2], R2, __fmaf_rn(cam->A[1], R1, __fmul_rn(cam->A[0], R0)));
     const float Q1 = __fmaf_rn(cam->A[5], R2, __fmaf_rn(cam->A[4], R1, __fmul_rn(cam->A[3], R0)));
     const float Q2 = __fmaf_rn(cam->A[8], R2, __fmaf_rn(cam->A[7], R1, __fmul_rn(cam->A[6], R0)));
+    __syncwarp();                                          // the previous view's readers are done
+    if (lane < 8) {
+      pixt[2 * lane] = make_float4(Q0, Q1, Q2, 0.0f);
+      pixt[2 * lane + 1] = make_float4(Q2, MU, SG, 0.0f);
+    }
+    __syncwarp();
     const int vb = v * p.B + b;
 
     // ---------------- projection of every hypothesis, bounding box of the tile's sample positions -------------
@@ -241,9 +248,9 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
     float xl = 1e9f, xh = -1e9f, yl = 1e9f, yh = -1e9f;
 #pragma unroll
     for (int i = 0; i < MTW; ++i) {
-      const float q0 = __shfl_sync(FULL, Q0, i), q1 = __shfl_sync(FULL, Q1, i), q2 = __shfl_sync(FULL, Q2, i);
+      const float4 t1 = pixt[2 * i], t2 = pixt[2 * i + 1];   // same address on every lane: broadcast
       float2 ix, iy, z;
-      project2(depth2(i), a0, a1, a2, q0, q1, q2, ix, iy, z);
+      project2(depth2(i, t2.y, t2.z), a0, a1, a2, t1.x, t1.y, t1.z, ix, iy, z);
       // anything left of -1 / right of W (above / below likewise) has all four taps out of the image: clamp so that
       // cells stay near the image and NaN (fmaxf drops it) maps to "out of bounds"
       ix.x = fminf(fmaxf(ix.x, -2.0f), xmax); ix.y = fminf(fmaxf(ix.y, -2.0f), xmax);
@@ -351,36 +358,46 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
           const float sxf = (float)sx, syf = (float)sy;
           const float xend = sx + stepx > wx1 ? 1e9f : (float)(sx + stepx), yend = sy + stepy > wy1 ? 1e9f : (float)(sy + stepy);
           const float pitch4f = (float)(nseg * 32);
+          const float c0f = MAGIC - 4.0f * sxf - pitch4f * syf;   // exact: integers below 2^24
           const uint32_t pitch4 = (uint32_t)nseg * 32u;
           uint32_t rowaddr = g_row0 + (uint32_t)(warp * 8 * gp) * 4u;
           float* accp = acc_s + lane * 65 + warp * 8;
 #pragma unroll
           for (int i = 0; i < MTW; ++i, rowaddr += (uint32_t)gp * 4u) {
             if (!((livemask >> i) & 1u)) continue;         // warp-uniform
+            // opaque to the optimiser: otherwise floor / fraction of all 8 pixels are hoisted out of the window loop
+            // (they do not depend on it) and held in 64 registers instead of recomputed with 6 instructions
+            asm volatile("" : "+f"(cix[i].x), "+f"(cix[i].y), "+f"(ciy[i].x), "+f"(ciy[i].y));
             const float2 x = cix[i], y = ciy[i];
-            const float x0a = floorf(x.x), x0b = floorf(x.y), y0a = floorf(y.x), y0b = floorf(y.y);
-            const float oa = __fmaf_rn(x0a - sxf, 4.0f, __fmaf_rn(y0a - syf, pitch4f, MAGIC));
-            const float ob = __fmaf_rn(x0b - sxf, 4.0f, __fmaf_rn(y0b - syf, pitch4f, MAGIC));
-            uint32_t ca = __float_as_uint(oa) & 0x3fffffu, cb = __float_as_uint(ob) & 0x3fffffu;
+            const float2 x0 = make_float2(floorf(x.x), floorf(x.y)), y0 = make_float2(floorf(y.x), floorf(y.y));
+            const float2 m1 = make_float2(-1.0f, -1.0f);
+            const float2 fx = __ffma2_rn(x0, m1, x), fy = __ffma2_rn(y0, m1, y);       // x - floor(x), exact
+            // byte offset of the cell in a G row = 4 * ((y0 - sy) * pitch + (x0 - sx)), in fp32 (small integers, exact)
+            // on top of 1.5 * 2^23 so that the integer sits in the mantissa
+            const float2 o = __ffma2_rn(y0, make_float2(pitch4f, pitch4f), __ffma2_rn(x0, make_float2(4.0f, 4.0f), make_float2(c0f, c0f)));
+            uint32_t ca = __float_as_uint(o.x) & 0x3fffffu, cb = __float_as_uint(o.y) & 0x3fffffu;
             bool pa = true, pb = true;
             if (!SINGLE) {                                 // evaluated in the sub-window that holds the cell origin
-              pa = x0a >= sxf && x0a < xend && y0a >= syf && y0a < yend;
-              pb = x0b >= sxf && x0b < xend && y0b >= syf && y0b < yend;
+              pa = x0.x >= sxf && x0.x < xend && y0.x >= syf && y0.x < yend;
+              pb = x0.y >= sxf && x0.y < xend && y0.y >= syf && y0.y < yend;
               ca = pa ? ca : 0u;                           // the others read cell 0
               cb = pb ? cb : 0u;
             }
             const uint32_t ga = rowaddr + ca, gb = rowaddr + cb;
-            const float ga00 = lds_f32(ga), ga01 = lds_f32(ga + 4), ga10 = lds_f32(ga + pitch4), ga11 = lds_f32(ga + pitch4 + 4);
-            const float gb00 = lds_f32(gb), gb01 = lds_f32(gb + 4), gb10 = lds_f32(gb + pitch4), gb11 = lds_f32(gb + pitch4 + 4);
-            const float fxa = x.x - x0a, fxb = x.y - x0b, fya = y.x - y0a, fyb = y.y - y0b;
-            const float costa = lerp2d(ga00, ga01, ga10, ga11, fxa, fya), costb = lerp2d(gb00, gb01, gb10, gb11, fxb, fyb);
+            const float2 g00 = make_float2(lds_f32(ga), lds_f32(gb)), g01 = make_float2(lds_f32(ga + 4), lds_f32(gb + 4));
+            const float2 g10 = make_float2(lds_f32(ga + pitch4), lds_f32(gb + pitch4));
+            const float2 g11 = make_float2(lds_f32(ga + pitch4 + 4), lds_f32(gb + pitch4 + 4));
+            const float2 ct = __ffma2_rn(fx, __ffma2_rn(g00, m1, g01), g00), cu = __ffma2_rn(fx, __ffma2_rn(g10, m1, g11), g10);
+            const float2 cost = __ffma2_rn(fy, __ffma2_rn(ct, m1, cu), ct);            // both hypotheses at once
+            const float costa = cost.x, costb = cost.y;
             bool oka, okb;
             if (CW) {
               const uint32_t ma = m_base + ca * 4u, mb = m_base + cb * 4u;
-              const float2 msa = lerp2d_x2(lds_f32x2(ma), lds_f32x2(ma + 16), lds_f32x2(ma + pitch4 * 4u), lds_f32x2(ma + pitch4 * 4u + 16), fxa, fya);
-              const float2 msb = lerp2d_x2(lds_f32x2(mb), lds_f32x2(mb + 16), lds_f32x2(mb + pitch4 * 4u), lds_f32x2(mb + pitch4 * 4u + 16), fxb, fyb);
-              const float q2 = __shfl_sync(FULL, Q2, i);
-              const float2 z = __fadd2_rn(make_float2(a2, a2), __fmul2_rn(make_float2(q2, q2), depth2(i)));
+              const float2 msa = lerp2d_x2(lds_f32x2(ma), lds_f32x2(ma + 16), lds_f32x2(ma + pitch4 * 4u), lds_f32x2(ma + pitch4 * 4u + 16), fx.x, fy.x);
+              const float2 msb = lerp2d_x2(lds_f32x2(mb), lds_f32x2(mb + 16), lds_f32x2(mb + pitch4 * 4u), lds_f32x2(mb + pitch4 * 4u + 16), fx.y, fy.y);
+              const float4 t2 = pixt[2 * i + 1];           // (q2, mu, sigma) of the pixel: broadcast
+              const float2 dd = depth2(i, t2.y, t2.z);
+              const float2 z = __fadd2_rn(make_float2(a2, a2), make_float2(__fmul_rn(t2.x, dd.x), __fmul_rn(t2.x, dd.y)));
               // homography.py:157-158: |z - mu~| < sigma~ * kappa, strict
               oka = fabsf(__fsub_rn(z.x, msa.x)) < __fmul_rn(msa.y, kappa);
               okb = fabsf(__fsub_rn(z.y, msb.x)) < __fmul_rn(msb.y, kappa);
@@ -422,7 +439,7 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
   }
   tmem_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, M_TMEM_COLS);
+  if (warp == 1) tmem_dealloc(tmem_base, M_TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

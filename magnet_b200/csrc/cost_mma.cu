@@ -34,6 +34,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstddef>
 #include <mutex>
 #include <type_traits>
@@ -97,6 +98,12 @@ __device__ __forceinline__ float lerp2d(float v00, float v01, float v10, float v
   return __fmaf_rn(fy, u - t, t);
 }
 
+// work counters of the persistent kernel: one slot per launch in flight (host ticket), re-armed by the last CTA of the
+// launch, so a captured launch can be replayed.  Launches that share a slot must not run concurrently.
+constexpr int MMA_SLOTS = 1024;
+__device__ unsigned g_mma_next[MMA_SLOTS];
+__device__ unsigned g_mma_done[MMA_SLOTS];
+
 // shared-memory loads by 32-bit shared address (the window / table offsets are computed as integers)
 __device__ __forceinline__ float lds_f32(uint32_t a) {
   float v;
@@ -120,7 +127,7 @@ template <int MODE, bool CW>
 __global__ void __launch_bounds__(MNT, 2)
 cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CUtensorMap tm_ref,
                 const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_meta, const int nchunks,
-                float* __restrict__ dbg) {
+                const int n_items, const int slot, float* __restrict__ dbg) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t padb = (1024u - (raw & 1023u)) & 1023u;
@@ -135,43 +142,67 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
   const unsigned FULL = 0xffffffffu;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.y;
   const int H = p.H, W = p.W, HW = p.HW, D = p.D, V = p.V;
   const int tiles_x = (W + MTW - 1) / MTW;
-  const int tile = blockIdx.x / nchunks;
-  const int jc = (blockIdx.x % nchunks) * MCH;
-  const int Dc = min(MCH, D - jc);
-  const int tx0 = (tile % tiles_x) * MTW, ty0 = (tile / tiles_x) * MTH;
+  const int items_per_b = tiles_x * ((H + MTH - 1) / MTH) * nchunks;
 
   const unsigned char* refbuf = reinterpret_cast<const unsigned char*>(p.ref_feat);
   const unsigned char* srcbuf = reinterpret_cast<const unsigned char*>(p.src_feat);
   const Split16Header* hdr_ref = reinterpret_cast<const Split16Header*>(refbuf);
   const Split16Header* hdr_src = reinterpret_cast<const Split16Header*>(srcbuf);
+  volatile int* next_item = reinterpret_cast<volatile int*>(smem + MOFF_BAR + 40);
 
+  // ---- once per CTA: barriers, tensor memory -----------------------------------------------------------------
   if (tid == 0) {
     mbar_init(bar_tma, 1);
     mbar_init(bar_mma, 1);
     mbar_init(bar_cam, 1);
     fence_mbar_init();
-    // first of all: camera table of the batch element (own barrier, needed first) and the reference tile, whose 16 KB
-    // complete on the window barrier, armed together with the first window (the transaction count may run negative
-    // until then).  Nothing else touches these regions.
-    mbar_arrive_expect_tx(bar_cam, (uint32_t)V * 64u);
-    bulk_load(sbase + MOFF_CAM, p.cams + (size_t)b * V, (uint32_t)V * 64u, bar_cam);
-    tma_load_5d(sbase + MOFF_A, &tm_ref, bar_tma, 0, tx0, ty0, 0, b);
+    prefetch_tmap(&tm_ref);
     prefetch_tmap(&tm_src);
     prefetch_tmap(&tm_meta);
   }
   if (warp == 1) tmem_alloc(sbase + MOFF_BAR + 32, M_TMEM_COLS);
   if (tid < 8) bbox[tid] = (tid & 1) ? -(1 << 28) : (1 << 28);       // [slot][x_lo, x_hi, y_lo, y_hi]
-  // lanes beyond the last hypothesis of the chunk replicate it (same sample position: inside every window, no
-  // predicates); their accumulator rows are never stored
-  if (tid < MCH) ks[tid] = MODE != MAGNET_DEPTH_VOLUME ? p.k[min(jc + tid, D - 1)] : 0.0f;
-  for (int idx = tid; idx < MCH * 65; idx += MNT) acc_s[idx] = 0.0f;
   tmem_fence_before_sync();
   __syncthreads();
   tmem_fence_after_sync();
   const uint32_t tmem_base = *reinterpret_cast<const volatile uint32_t*>(smem + MOFF_BAR + 32);
+  uint32_t ph_tma = 0, ph_mma = 0, ph_cam = 0;
+  int it = 0;
+  int cur_b = -1;
+  const float xmax = (float)W + 1.0f, ymax = (float)H + 1.0f;
+  const float kappa = p.kappa;
+  const uint32_t g_row0 = sbase + MOFF_R, m_base = sbase + MOFF_META;
+
+  // ---- persistent CTA: work items (batch element, tile, hypothesis chunk) are handed out dynamically -----------
+  // (the first one is the block index, the others come from a global counter: no tail of a partial last wave, barriers
+  // and tensor memory set up once per SM slot)
+  int item = blockIdx.x;
+  while (item < n_items) {
+  const int b = item / items_per_b;
+  const int rem = item - b * items_per_b;
+  const int tile = rem / nchunks;
+  const int jc = (rem - tile * nchunks) * MCH;
+  const int Dc = min(MCH, D - jc);
+  const int tx0 = (tile % tiles_x) * MTW, ty0 = (tile / tiles_x) * MTH;
+
+  if (tid == 0) {
+    // first of all: the camera table when the batch element changes (own barrier, needed first) and the reference
+    // tile, whose 16 KB complete on the window barrier, armed together with the first window (the transaction count
+    // may run negative until then).  Every reader of these regions passed the barrier that ended the previous item.
+    if (b != cur_b) {
+      mbar_arrive_expect_tx(bar_cam, (uint32_t)V * 64u);
+      bulk_load(sbase + MOFF_CAM, p.cams + (size_t)b * V, (uint32_t)V * 64u, bar_cam);
+    }
+    tma_load_5d(sbase + MOFF_A, &tm_ref, bar_tma, 0, tx0, ty0, 0, b);
+    *next_item = (int)gridDim.x + (int)atomicAdd(&g_mma_next[slot], 1u);   // read after the barrier that ends the item
+  }
+  // lanes beyond the last hypothesis of the chunk replicate it (same sample position: inside every window, no
+  // predicates); their accumulator rows are never stored
+  if (tid < MCH) ks[tid] = MODE != MAGNET_DEPTH_VOLUME ? p.k[min(jc + tid, D - 1)] : 0.0f;
+  for (int idx = tid; idx < MCH * 65; idx += MNT) acc_s[idx] = 0.0f;
+  __syncthreads();
 
   // ---- per-warp constants: lane i (mod 8) holds the ray / Gaussian of pixel i of my tile row ----------------
   const int py = ty0 + warp;
@@ -219,13 +250,12 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
   };
   float4* pixt = reinterpret_cast<float4*>(smem + MOFF_PIX) + warp * 16;
 
-  mbar_wait_or_trap(bar_cam, 0);                           // camera table landed
-  uint32_t ph_tma = 0, ph_mma = 0;
+  if (b != cur_b) {                                        // CTA-uniform: camera table landed
+    mbar_wait_or_trap(bar_cam, ph_cam);
+    ph_cam ^= 1u;
+    cur_b = b;
+  }
   bool first = true;                                       // the first window also waits for the reference tile
-  int it = 0;
-  const float xmax = (float)W + 1.0f, ymax = (float)H + 1.0f;
-  const float kappa = p.kappa;
-  const uint32_t g_row0 = sbase + MOFF_R, m_base = sbase + MOFF_META;
 
   for (int v = 0; v < V; ++v) {
     const magnet_camera* cam = cams_s + v;                 // V <= MMAXV is checked on the host
@@ -340,7 +370,7 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
         tmem_fence_before_sync();
         __syncthreads();
 #ifdef MAGNET_MMA_DEBUG
-        if (dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && it == 1 && sy == wy0 && sx == wx0) {
+        if (dbg != nullptr && item == 0 && v == 0 && sy == wy0 && sx == wx0) {
           if (tid == 0) {
             dbg[0] = (float)sx; dbg[1] = (float)sy; dbg[2] = (float)nseg; dbg[3] = (float)rows; dbg[4] = (float)npad;
             dbg[5] = (float)gp; dbg[6] = (float)v; dbg[7] = 3.0f; dbg[8] = hdr_ref->scale; dbg[9] = hdr_src->scale;
@@ -422,19 +452,43 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
   if (first) {                                             // no valid view: the reference-tile copy is still in flight
     if (tid == 0) mbar_arrive_expect_tx(bar_tma, 16384u);
     mbar_wait_or_trap(bar_tma, ph_tma);
+    ph_tma ^= 1u;
   }
 
   // -------- epilogue: undo the split scales, 1/V mean over ALL views (homography.py:120), coalesced store --------
   {
     const float inv = hdr_ref->inv_scale * hdr_src->inv_scale;   // powers of two: exact
     const bool exact = p.inv_v_exact != 0.0f;              // V a power of two: the division is an exact scaling
-    for (int idx = tid; idx < MCH * MPX; idx += MNT) {
-      const int j = idx >> 6, pp = idx & 63;
-      const int y = ty0 + (pp >> 3), x = tx0 + (pp & 7);
-      if (j < Dc && x < W && y < H) {
-        const float a = acc_s[j * 65 + pp] * inv;
-        p.out[((size_t)b * D + jc + j) * HW + (size_t)y * W + x] = exact ? a * p.inv_v_exact : __fdiv_rn(a, p.vf);
+    auto fin = [&](float a) { a *= inv; return exact ? a * p.inv_v_exact : __fdiv_rn(a, p.vf); };
+    if ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
+      for (int idx = tid; idx < MCH * 16; idx += MNT) {    // (hypothesis, tile row, half row): one 16-byte store
+        const int j = idx >> 4, r = (idx >> 1) & 7, hx = (idx & 1) * 4;
+        const int y = ty0 + r, x = tx0 + hx;
+        if (j < Dc && x < W && y < H) {
+          const float* a = acc_s + j * 65 + r * 8 + hx;
+          *reinterpret_cast<float4*>(p.out + ((size_t)b * D + jc + j) * HW + (size_t)y * W + x) =
+              make_float4(fin(a[0]), fin(a[1]), fin(a[2]), fin(a[3]));
+        }
       }
+    } else {
+      for (int idx = tid; idx < MCH * MPX; idx += MNT) {
+        const int j = idx >> 6, pp = idx & 63;
+        const int y = ty0 + (pp >> 3), x = tx0 + (pp & 7);
+        if (j < Dc && x < W && y < H) p.out[((size_t)b * D + jc + j) * HW + (size_t)y * W + x] = fin(acc_s[j * 65 + pp]);
+      }
+    }
+  }
+  const int nxt = *next_item;                              // written by thread 0 when this item began
+  __syncthreads();                                         // accumulators and tables are free; next_item may be rewritten
+  item = nxt;
+  }  // work items
+
+  if (tid == 0) {                                          // the last CTA to finish re-arms the work counter
+    __threadfence();
+    if (atomicAdd(&g_mma_done[slot], 1u) == gridDim.x - 1) {
+      g_mma_next[slot] = 0u;
+      g_mma_done[slot] = 0u;
+      __threadfence();
     }
   }
   tmem_fence_before_sync();
@@ -567,6 +621,17 @@ static float* g_mma_dbg = nullptr;
 void mma_set_debug_buffer(float* p) { g_mma_dbg = p; }
 #endif
 
+static int sm_count(int dev) {
+  static int cached[64] = {0};
+  int& c = cached[dev & 63];
+  if (c == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    c = n;
+  }
+  return c;
+}
+
 template <int MODE, bool CW>
 static cudaError_t launch_mma_mw(const CostParams& p, cudaStream_t st) {
   static std::once_flag flags[64];
@@ -590,12 +655,15 @@ static cudaError_t launch_mma_mw(const CostParams& p, cudaStream_t st) {
   if ((e = make_meta_map(&tm_meta, srcbuf + SPLIT16_HEADER + (size_t)N * p.HW * 256, N, p.H, p.W)) != cudaSuccess) return e;
   const int nchunks = (p.D + MCH - 1) / MCH;
   const int tiles = ((p.W + MTW - 1) / MTW) * ((p.H + MTH - 1) / MTH);
-  dim3 grid(tiles * nchunks, p.B), block(MNT);
+  const int n_items = tiles * nchunks * p.B;
+  static std::atomic<unsigned> ticket{0};
+  const int slot = (int)(ticket.fetch_add(1) % MMA_SLOTS);
+  dim3 grid(std::min(n_items, 2 * sm_count(dev))), block(MNT);   // persistent: two CTAs per SM
   float* dbg = nullptr;
 #ifdef MAGNET_MMA_DEBUG
   dbg = g_mma_dbg;
 #endif
-  kern<<<grid, block, M_SMEM_TOTAL, st>>>(p, tm_ref, tm_src, tm_meta, nchunks, dbg);
+  kern<<<grid, block, M_SMEM_TOTAL, st>>>(p, tm_ref, tm_src, tm_meta, nchunks, n_items, slot, dbg);
   return cudaGetLastError();
 }
 
@@ -604,7 +672,9 @@ bool mma_supports(int C, int D, int V, int layout) {
 }
 
 void mma_launch_info(int B, int H, int W, int D, int* grid, int* block, int* smem) {
-  *grid = ((W + MTW - 1) / MTW) * ((H + MTH - 1) / MTH) * ((D + MCH - 1) / MCH) * B;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  *grid = std::min(((W + MTW - 1) / MTW) * ((H + MTH - 1) / MTH) * ((D + MCH - 1) / MCH) * B, 2 * sm_count(dev));
   *block = MNT;
   *smem = M_SMEM_TOTAL;
 }

@@ -56,12 +56,13 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(workload, tma=False):
+def ncu_traffic(workload, kind=""):
     """DRAM bytes per launch of the timed cost kernel from the committed ncu --set full capture (profiles/traffic.json:
-    keys "<config>" for the global-gather kernel, "<config>:tma" for the TMA-staged one), or None."""
+    keys "<config>:mma" for the tensor-core kernel, "<config>" for the global-gather kernel, "<config>:tma" for the
+    TMA-staged one), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(workload + (":tma" if tma else ""))
+            return json.load(f).get(workload + (":" + kind if kind else ""))
     except Exception:
         return None
 
@@ -247,7 +248,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--variant", default="auto", choices=["auto", "direct", "cells", "cells_noreuse", "tma"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "direct", "cells", "cells_noreuse", "tma", "mma"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gnet", action="store_true")
     args = ap.parse_args()
@@ -269,7 +270,7 @@ def main():
     from magnet_b200 import _lib, ops
     from magnet_b200.synthetic import make_config
     variant = {"auto": _lib.VARIANT_AUTO, "direct": _lib.VARIANT_DIRECT, "cells": _lib.VARIANT_CELLS,
-               "cells_noreuse": _lib.VARIANT_CELLS_NOREUSE, "tma": _lib.VARIANT_TMA}[args.variant]
+               "cells_noreuse": _lib.VARIANT_CELLS_NOREUSE, "tma": _lib.VARIANT_TMA, "mma": _lib.VARIANT_MMA}[args.variant]
 
     # Weak scaling = the SAME work on every GPU: all ranks build the same seeded batch (each owns its own copy).  With
     # per-rank seeds the step time followed the poses drawn (the kernel's cost depends on how many bilinear cells a
@@ -287,16 +288,29 @@ def main():
     is_valid_d = inp.is_valid.to(dev)
     intM_d = inp.cam_intrins['intM'].to(dev)
     rays_d = inp.cam_intrins['unit_ray_array_2D'].to(dev).contiguous()
-    pixc = variant == _lib.VARIANT_TMA                               # TMA-staged kernel: PIXC; global-gather kernels: TILED32
-    layout = _lib.SRC_PIXC if pixc else _lib.SRC_TILED32
-    src_packed = (torch.empty(V * B, H, Wd, C + 4, device=dev) if pixc
-                  else torch.empty(V * B, H, (Wd + 31) // 32, C // 4, 32, 4, device=dev))
+    # production (auto): the tensor-core kernel on fp16 hi/lo planes when C == 64; TMA-staged kernel: PIXC;
+    # global-gather kernels: TILED32
+    split = variant == _lib.VARIANT_MMA or (variant == _lib.VARIANT_AUTO and C == 64 and V <= 16)
+    pixc = variant == _lib.VARIANT_TMA
+    layout = _lib.SRC_SPLIT16 if split else (_lib.SRC_PIXC if pixc else _lib.SRC_TILED32)
+    kind = "mma" if split else ("tma" if pixc else "")
+    ref_split = None
+    if split:
+        src_packed = torch.empty(int(_lib.lib().magnet_split16_bytes(V * B, H, Wd)), device=dev, dtype=torch.uint8)
+        ref_split = torch.empty(int(_lib.lib().magnet_split16_bytes(B, H, Wd)), device=dev, dtype=torch.uint8)
+    elif pixc:
+        src_packed = torch.empty(V * B, H, Wd, C + 4, device=dev)
+    else:
+        src_packed = torch.empty(V * B, H, (Wd + 31) // 32, C // 4, 32, 4, device=dev)
     cv = torch.empty(B, D, H, Wd, device=dev)
     ev_pairs = []
 
     def hot_step(record=False):
         """repack + camera table + N_ITER x (fused cost kernel -> update kernel); everything device-resident."""
-        if pixc:
+        if split:                                           # both feature sets, once per step
+            ops.repack_split16(g.nghbr_feat, g.nghbr_gmms, out=src_packed)
+            ops.repack_split16(g.ref_feat, out=ref_split)
+        elif pixc:
             ops.repack_pixc(g.nghbr_feat, g.nghbr_gmms, out=src_packed)
         else:
             ops.repack_tiled32(g.nghbr_feat, out=src_packed)
@@ -312,7 +326,8 @@ def main():
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
             ops.cost_volume(g.ref_feat, src_packed, rays_d, cams, V=V, src_layout=layout, consistency=True,
-                            src_gmm=g.nghbr_gmms, kappa=float(inp.thres), ref_gmm=pred, k=karr, out=cv, variant=variant)
+                            src_gmm=g.nghbr_gmms, kappa=float(inp.thres), ref_gmm=pred, k=karr, out=cv, variant=variant,
+                            ref_split=ref_split)
             if record:
                 e1.record()
                 ev_pairs.append((e0, e1))
@@ -512,9 +527,10 @@ def main():
     peak, peak_src = measured_peak()
     abytes = algorithmic_bytes(B, V, D, C, HW, fused=True)
     achieved = abytes / (kern_ms * 1e-3) / 1e9
-    grid, block, smem = ops.cost_launch_info(B, V, D, C, H, Wd, variant=_lib.VARIANT_CELLS if variant == _lib.VARIANT_CELLS_NOREUSE else variant)
+    info_variant = _lib.VARIANT_MMA if split else (_lib.VARIANT_CELLS if variant in (_lib.VARIANT_CELLS_NOREUSE, _lib.VARIANT_AUTO) else variant)
+    grid, block, smem = ops.cost_launch_info(B, V, D, C, H, Wd, variant=info_variant)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(args.config, tma=pixc), "kernel": {_lib.VARIANT_DIRECT: "cost_direct_kernel<CW>", _lib.VARIANT_CELLS: "cost_cells_kernel<64,GAUSS,CW> (TILED32 gather)",
+                "traffic": ncu_traffic(args.config, kind), "kernel": "cost_mma_kernel<GAUSS,CW> (SPLIT16 planes, tcgen05.mma + TMA windows)" if split else {_lib.VARIANT_DIRECT: "cost_direct_kernel<CW>", _lib.VARIANT_CELLS: "cost_cells_kernel<64,GAUSS,CW> (TILED32 gather)",
                            _lib.VARIANT_CELLS_NOREUSE: "cost_cells_kernel<64,GAUSS,CW,noreuse>",
                            _lib.VARIANT_TMA: "cost_tma_kernel<64,GAUSS,CW> (PIXC layout, TMA-staged window)"}.get(
                                variant, "cost_cells_kernel<64,GAUSS,CW> (TILED32 gather)"),

@@ -500,15 +500,22 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
 // MAGNET_SRC_SPLIT16 producer: (N, 64, H, W) fp32 [+ (N, 2, H, W) Gaussians] ->
 //   header | fp16 planes (N, 2, H, W, 64): hi = fp16(x*s), lo = fp16(x*s - hi) | table (N, H, W, 4) = (mu, sigma, 0, 0)
 // ---------------------------------------------------------------------------------------------------------------
+// bits of |x|, 0 for inf / NaN: the scale is chosen from the finite values, non-finite elements poison only their own
+// products
+__device__ __forceinline__ unsigned finite_abs_bits(float x) {
+  const unsigned u = __float_as_uint(x) & 0x7fffffffu;
+  return u >= 0x7f800000u ? 0u : u;
+}
+
 __global__ void __launch_bounds__(256) absmax_kernel(const float4* __restrict__ x, size_t n4, const float* __restrict__ tail,
                                                      int ntail, unsigned* __restrict__ out) {
   unsigned m = 0u;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     const float4 v = __ldg(x + i);
-    m = max(max(m, __float_as_uint(v.x) & 0x7fffffffu), __float_as_uint(v.y) & 0x7fffffffu);
-    m = max(max(m, __float_as_uint(v.z) & 0x7fffffffu), __float_as_uint(v.w) & 0x7fffffffu);
+    m = max(max(m, finite_abs_bits(v.x)), finite_abs_bits(v.y));
+    m = max(max(m, finite_abs_bits(v.z)), finite_abs_bits(v.w));
   }
-  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) m = max(m, __float_as_uint(tail[threadIdx.x]) & 0x7fffffffu);
+  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) m = max(m, finite_abs_bits(tail[threadIdx.x]));
   m = __reduce_max_sync(0xffffffffu, m);
   if ((threadIdx.x & 31) == 0 && m != 0u) atomicMax(out, m);
 }

@@ -11,8 +11,9 @@ per-(batch, view) Python loop):
     cached across the N_iter calls of one forward (keyed by object identity + version counter);
   * ``R`` / ``t`` arrive as non-contiguous views of ``nghbr_poses`` (MAGNET.py:147-148): passed to
     ``magnet_pack_cameras_f32`` with their strides, no copy;
-  * ``nghbr_feat`` / ``nghbr_gmms`` arrive NCHW: repacked once per forward into the pixel-major PIXC layout the
-    TMA-staged kernel fetches its windows from (cached the same way; bypassed under CUDA-graph capture).
+  * ``nghbr_feat`` / ``nghbr_gmms`` / ``ref_feat`` arrive NCHW: split once per forward into the fp16 hi/lo planes the
+    tensor-core kernel's TMA boxes fetch (C == 64; else the pixel-major PIXC layout of the TMA-staged CUDA-core kernel;
+    cached the same way; bypassed under CUDA-graph capture).
 The CW volume is not differentiable (its inputs never require grad in the reference, SURVEY §3.2);
 the F volume is differentiable w.r.t. both feature maps (magnet_cost_volume_f_bwd_f32) for F-Net training.
 """
@@ -119,30 +120,47 @@ def _camera_table(cam_intrins, R, t, is_valid, device):
     return _cache.put("cams", src, ops.pack_cameras(intM_d, R, t, valid_d), extra)
 
 
+def _wants_split16(C: int, V: int, variant: int) -> bool:
+    return variant in (_lib.VARIANT_AUTO, _lib.VARIANT_MMA) and C == 64 and V <= 16
+
+
 def _wants_pixc(C: int, V: int, variant: int) -> bool:
     return variant in (_lib.VARIANT_AUTO, _lib.VARIANT_TMA) and C in (16, 32, 64) and V <= 16
 
 
-def _packed_source(nghbr_feat, nghbr_gmms, V, variant):
+def _packed_source(nghbr_feat, nghbr_gmms, V, variant, ref_feat=None):
     """The source maps in the layout the selected kernel reads, repacked once per forward (cached on the caller's
-    tensor objects): PIXC (features + Gaussians, pixel-major) for the TMA production kernel, TILED32 for the
-    global-gather cross-check kernels, NCHW when the channel count fits neither."""
+    tensor objects): SPLIT16 (fp16 hi/lo planes + Gaussian table, also of the reference features) for the tensor-core
+    production kernel, PIXC (features + Gaussians, pixel-major) for the TMA-staged CUDA-core kernel, TILED32 for the
+    global-gather kernels, NCHW when the channel count fits none.  Returns (source, layout, reference split or None)."""
     C = nghbr_feat.shape[1]
+    if _wants_split16(C, V, variant) and ref_feat is not None:
+        src = (nghbr_feat,) if nghbr_gmms is None else (nghbr_feat, nghbr_gmms)
+        hit = _cache.get("split16", src)
+        if hit is None:
+            hit = _cache.put("split16", src, ops.repack_split16(nghbr_feat.detach(),
+                                                                None if nghbr_gmms is None else nghbr_gmms.detach()))
+        ref = _cache.get("split16ref", (ref_feat,))
+        if ref is None:
+            ref = _cache.put("split16ref", (ref_feat,), ops.repack_split16(ref_feat.detach()))
+        return hit, _lib.SRC_SPLIT16, ref
+    if variant == _lib.VARIANT_MMA:
+        raise _lib.MagnetError(f"MAGNET_VARIANT_MMA needs C == 64 and V <= 16, got C={C}, V={V}")
     if _wants_pixc(C, V, variant):
         src = (nghbr_feat,) if nghbr_gmms is None else (nghbr_feat, nghbr_gmms)
         hit = _cache.get("pixc", src)
         if hit is None:
             hit = _cache.put("pixc", src, ops.repack_pixc(nghbr_feat.detach(),
                                                           None if nghbr_gmms is None else nghbr_gmms.detach()))
-        return hit, _lib.SRC_PIXC
+        return hit, _lib.SRC_PIXC, None
     if variant == _lib.VARIANT_TMA:
         raise _lib.MagnetError(f"MAGNET_VARIANT_TMA needs C in (16, 32, 64) and V <= 16, got C={C}, V={V}")
     if C % 4 != 0:
-        return nghbr_feat.detach().contiguous(), _lib.SRC_NCHW
+        return nghbr_feat.detach().contiguous(), _lib.SRC_NCHW, None
     hit = _cache.get("tiled32", (nghbr_feat,))
     if hit is None:
         hit = _cache.put("tiled32", (nghbr_feat,), ops.repack_tiled32(nghbr_feat.detach()))
-    return hit, _lib.SRC_TILED32
+    return hit, _lib.SRC_TILED32, None
 
 
 def est_costvolume_CW(d_volume, ref_feat, nghbr_feat, ref_gmms, nghbr_gmms,
@@ -160,10 +178,10 @@ def est_costvolume_CW(d_volume, ref_feat, nghbr_feat, ref_gmms, nghbr_gmms,
     with torch.no_grad():
         _, rays_d = _device_intrinsics(cam_intrins, device)
         cams = _camera_table(cam_intrins, R, t, is_valid, device)
-        src, layout = _packed_source(nghbr_feat, nghbr_gmms, V, variant)
+        src, layout, ref_split = _packed_source(nghbr_feat, nghbr_gmms, V, variant, ref_feat)
         return ops.cost_volume(ref_feat.detach(), src, rays_d, cams, V=V, src_layout=layout, consistency=True,
                                src_gmm=nghbr_gmms.detach(), kappa=float(thres), d_volume=d_volume.detach(),
-                               variant=variant)
+                               variant=variant, ref_split=ref_split)
 
 
 def _plane_list(d_center):
@@ -180,9 +198,9 @@ class _CostVolumeF(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, ref_feat, nghbr_feat, planes, rays_d, cams, V, variant):
-        src, layout = _packed_source(nghbr_feat, None, V, variant)
+        src, layout, ref_split = _packed_source(nghbr_feat, None, V, variant, ref_feat)
         out = ops.cost_volume(ref_feat.detach(), src, rays_d, cams, V=V, src_layout=layout, consistency=False,
-                              k=planes, planes=True, softmax=True, variant=variant)
+                              k=planes, planes=True, softmax=True, variant=variant, ref_split=ref_split)
         ctx.save_for_backward(ref_feat.detach(), nghbr_feat.detach(), out, rays_d, cams)
         ctx.planes, ctx.V = planes, V
         return out

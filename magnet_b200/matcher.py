@@ -58,7 +58,7 @@ class MatchingPlan:
     device intrinsics / rays, camera-constant table, source features in the gather layout."""
 
     def __init__(self, ref_feat, nghbr_feat, nghbr_gmms, nghbr_poses, is_valid, cam_intrins, *,
-                 thres: int = 5, src_layout: int = _lib.SRC_TILED32):
+                 thres: int = 5, src_layout: int = _lib.SRC_SPLIT16):
         dev = ref_feat.device
         self.B, self.C, self.H, self.W = ref_feat.shape
         self.V = nghbr_feat.shape[0] // self.B
@@ -72,8 +72,11 @@ class MatchingPlan:
         self._nghbr_feat = nghbr_feat.detach()
         self._packed = {}
         self._ref_split = None
-        # Sampler-fused loop: the global-gather kernel (TILED32) is the faster one at every measured size (profiles/
-        # r2_kernels.md); pass src_layout=SRC_PIXC / variant=VARIANT_TMA for the TMA-staged kernel.
+        # Production: the tensor-core kernel on the fp16 hi/lo planes (C == 64); otherwise the global-gather kernel
+        # (TILED32), the faster CUDA-core one at every measured size (profiles/r2_kernels.md).  Pass
+        # src_layout=SRC_PIXC / variant=VARIANT_TMA for the TMA-staged CUDA-core kernel.
+        if src_layout == _lib.SRC_SPLIT16 and not (self.C == 64 and self.V <= 16):
+            src_layout = _lib.SRC_TILED32
         if src_layout == _lib.SRC_PIXC and not (self.C in (16, 32, 64) and self.V <= 16):
             src_layout = _lib.SRC_TILED32
         if src_layout == _lib.SRC_TILED32 and self.C % 4 != 0:

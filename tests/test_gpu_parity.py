@@ -16,7 +16,14 @@ from tests.util import compare_volume, golden_inputs, load_golden, oracle_cw
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [("direct", _lib.VARIANT_DIRECT), ("cells", _lib.VARIANT_CELLS), ("tma", _lib.VARIANT_TMA)]
+VARIANTS = [("direct", _lib.VARIANT_DIRECT), ("cells", _lib.VARIANT_CELLS), ("tma", _lib.VARIANT_TMA),
+            ("mma", _lib.VARIANT_MMA)]
+
+
+def _skip_unsupported(variant, C):
+    """The tensor-core kernel is instantiated for C == 64 only (the F-Net width, BASELINE.json configs)."""
+    if variant == _lib.VARIANT_MMA and C != 64:
+        pytest.skip("MAGNET_VARIANT_MMA: C == 64 only")
 
 
 def _run_cw(inp, dvol, dev, variant):
@@ -32,6 +39,7 @@ def _run_cw(inp, dvol, dev, variant):
 def test_cw_matches_reference_golden(cuda, name, vname, variant):
     """The reference's own outputs (frozen in tests/golden) are the pin; the oracle supplies flip margins."""
     z, inp = golden_inputs(name)
+    _skip_unsupported(variant, inp.ref_feat.shape[1])
     dvol = torch.from_numpy(mo.depth_sampler(inp.ref_gmms[:, 0].numpy(), inp.ref_gmms[:, 1].numpy(), z["k_list"]))
     got = _run_cw(inp, dvol, cuda, variant)
     _, margin = oracle_cw(inp, dvol.numpy(), return_margin=True)
@@ -43,6 +51,7 @@ def test_cw_matches_reference_golden(cuda, name, vname, variant):
 @pytest.mark.parametrize("case", sorted(kat.CW_CASES))
 def test_cw_known_answers_gpu(cuda, case, vname, variant):
     inp, dvol, exp, tol = kat.CW_CASES[case]()
+    _skip_unsupported(variant, inp.ref_feat.shape[1])
     got = _run_cw(inp, dvol, cuda, variant)
     if tol == 0.0:
         assert np.array_equal(got, exp.astype(np.float32))
@@ -66,7 +75,7 @@ def test_cw_vs_oracle_seeded(cuda, seed, depth, shape):
     dvol = inp.depth_volume()
     want, margin = oracle_cw(inp, dvol.numpy(), return_margin=True)
     for vname, variant in VARIANTS:
-        if variant != _lib.VARIANT_DIRECT and shape["C"] not in (16, 32, 64):
+        if (variant != _lib.VARIANT_DIRECT and shape["C"] not in (16, 32, 64)) or (variant == _lib.VARIANT_MMA and shape["C"] != 64):
             with pytest.raises(_lib.MagnetError):
                 _run_cw(inp, dvol, cuda, variant)
             continue
@@ -112,6 +121,67 @@ def test_tma_kernel_fuzz_against_direct_kernel(cuda):
     print("fuzz: worst fraction of threshold-adjacent elements", worst)
 
 
+def test_mma_kernel_fuzz_against_direct_kernel(cuda):
+    """Randomised shapes / poses for the tensor-core kernel against the reference-order direct kernel (both depth modes):
+    ragged tiles, 1..6 views with invalid ones, 1..150 planes (partial and multiple 64-hypothesis chunks), large baselines
+    and random depths (windows beyond 256 cells -> sub-windows), both camera families, feature scales from 1e-3 to 1e3
+    (the power-of-two split scale).  No oracle here, so elements on the consistency threshold are budgeted."""
+    rng = np.random.default_rng(4048)
+    worst = 0.0
+    for it in range(24):
+        B, V = int(rng.integers(1, 3)), int(rng.integers(1, 7))
+        D = int(rng.choice([1, 3, 5, 17, 33, 64, 65, 150])) if it % 3 else int(rng.integers(1, 70))
+        H, W = int(rng.integers(5, 41)), int(rng.integers(5, 71))
+        depth = "random" if it % 4 == 0 else "smooth"
+        family = "kitti" if it % 5 == 0 else "scannet"
+        kw = dict(rot_deg=float(rng.uniform(1, 14)), trans=float(rng.uniform(0.05, 0.7))) if it % 2 else {}
+        invalid = [(0, int(rng.integers(0, V)))] if V > 1 and it % 3 == 0 else ()
+        inp = make_inputs(B=B, V=V, D=D, H=H, W=W, C=64, seed=3000 + it, depth=depth, family=family, invalid=invalid, **kw)
+        scale = float(10.0 ** rng.integers(-3, 4))
+        inp.ref_feat.mul_(scale)
+        inp.nghbr_feat.mul_(1.0 / scale if it % 2 else scale)
+        g = inp.to(cuda)
+        plan = magnet_b200.MatchingPlan(g.ref_feat, g.nghbr_feat, g.nghbr_gmms, g.nghbr_poses, inp.is_valid,
+                                        inp.cam_intrins, thres=inp.thres)
+        assert plan.layout == _lib.SRC_SPLIT16
+        k = inp.k.tolist()
+        want = plan.cost(g.ref_gmms, k, variant=_lib.VARIANT_DIRECT)
+        dvol = ops.sample_depths(g.ref_gmms, k)
+        for mode, got in (("fused", plan.cost(g.ref_gmms, k)),
+                          ("drop-in", magnet_b200.est_costvolume_CW(dvol, g.ref_feat, g.nghbr_feat, g.ref_gmms, g.nghbr_gmms,
+                                                                      g.R, g.t, inp.is_valid, inp.cam_intrins, inp.thres))):
+            assert torch.isfinite(got).all(), (it, mode)
+            sc = max(float(want.abs().max()), 1e-20)
+            d = (got - want).abs()
+            frac = float((d > 1e-4 * sc).float().mean())
+            worst = max(worst, frac)
+            assert frac <= 2e-3 and float(d.median()) <= 1e-5 * sc, (it, mode, dict(B=B, V=V, D=D, H=H, W=W, depth=depth), frac)
+    print("mma fuzz: worst fraction of threshold-adjacent elements", worst)
+
+
+def test_mma_launch_is_graph_replayable(cuda):
+    """The persistent tensor-core kernel hands out work through a global counter that its last CTA re-arms: a captured
+    launch must replay (several times, with new inputs) and agree with an eager launch bit for bit."""
+    inp = make_inputs(B=2, V=3, D=64, H=40, W=56, C=64, seed=92, depth="smooth").to(cuda)
+    plan = magnet_b200.MatchingPlan(inp.ref_feat, inp.nghbr_feat, inp.nghbr_gmms, inp.nghbr_poses, inp.is_valid,
+                                    inp.cam_intrins, thres=5)
+    k = ops.k_array(inp.k.tolist())
+    gmm = inp.ref_gmms.clone()
+    cv = torch.empty(2, 64, 40, 56, device=cuda)
+    plan.cost(gmm, k, out=cv)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        plan.cost(gmm, k, out=cv)
+    for rep_ in range(3):
+        gmm.copy_(inp.ref_gmms * (1.0 + 0.01 * rep_))
+        graph.replay()
+        torch.cuda.synchronize()
+        got = cv.clone()
+        want = plan.cost(gmm, k)
+        assert torch.equal(got, want), rep_
+
+
 def test_fused_sampler_equals_drop_in(cuda):
     """MAGNET_DEPTH_GAUSS (sampler fused, analytic cell walk) against MAGNET_DEPTH_VOLUME (drop-in, exact
     per-hypothesis cell walk): d_j is formed with the same separately rounded multiply and add (MAGNET.py:155);
@@ -147,6 +217,7 @@ def test_fused_sampler_equals_drop_in(cuda):
 @pytest.mark.parametrize("name", ["cw_small_random", "cw_c64_d64", "cw_kitti"])
 def test_f_volume_matches_reference_golden(cuda, name, vname, variant):
     z, inp = golden_inputs(name)
+    _skip_unsupported(variant, inp.ref_feat.shape[1])
     g = inp.to(cuda)
     dc = torch.from_numpy(z["planes"]).view(1, -1, 1, 1).to(cuda)
     got = magnet_b200.est_costvolume_F(dc, g.ref_feat, g.nghbr_feat, g.R, g.t, inp.is_valid, inp.cam_intrins,
@@ -293,16 +364,16 @@ def test_non_finite_inputs_stated_deviation(cuda):
     exactly 0 in both.  Pinned here: wherever the reference is finite, the kernel is finite and within the tolerance;
     where the reference is non-finite, the kernel is either non-finite or finite (rejected) — reported, not hidden."""
     from oracle import torch_ref
-    inp = make_inputs(B=1, V=2, D=16, H=16, W=24, C=16, seed=83, depth="smooth")
-    inp.nghbr_feat[0, 3, 5, 7] = float("inf")
-    inp.nghbr_feat[1, 0, 9, 11] = float("nan")
-    g = inp.to(cuda)
-    cam_d = {k: v.to(cuda) for k, v in inp.cam_intrins.items()}
-    dvol = inp.depth_volume().to(cuda)
-    with torch.no_grad():
-        want = torch_ref.cost_volume_cw(dvol, g.ref_feat, g.nghbr_feat, g.ref_gmms, g.nghbr_gmms, g.R, g.t, inp.is_valid,
-                                        cam_d, inp.thres)
-        for vname, variant in VARIANTS[1:]:
+    for vname, variant in VARIANTS[1:]:
+        inp = make_inputs(B=1, V=2, D=16, H=16, W=24, C=64 if variant == _lib.VARIANT_MMA else 16, seed=83, depth="smooth")
+        inp.nghbr_feat[0, 3, 5, 7] = float("inf")
+        inp.nghbr_feat[1, 0, 9, 11] = float("nan")
+        g = inp.to(cuda)
+        cam_d = {k: v.to(cuda) for k, v in inp.cam_intrins.items()}
+        dvol = inp.depth_volume().to(cuda)
+        with torch.no_grad():
+            want = torch_ref.cost_volume_cw(dvol, g.ref_feat, g.nghbr_feat, g.ref_gmms, g.nghbr_gmms, g.R, g.t, inp.is_valid,
+                                            cam_d, inp.thres)
             got = magnet_b200.est_costvolume_CW(dvol, g.ref_feat, g.nghbr_feat, g.ref_gmms, g.nghbr_gmms, g.R, g.t,
                                                 inp.is_valid, inp.cam_intrins, inp.thres, variant=variant)
             fin = torch.isfinite(want)
@@ -440,7 +511,7 @@ def test_points_behind_the_source_camera(cuda, vname, variant):
     """The reference has no positive-depth test: hypotheses behind a source camera are projected and
     sampled like any other.  A source view translated 3 m forward puts about half of them behind it; the analytic
     cell walk must hand those lanes to the exact walk, and the result must still match the oracle."""
-    inp = make_inputs(B=1, V=2, D=32, H=16, W=24, C=16, seed=81, depth="smooth")
+    inp = make_inputs(B=1, V=2, D=32, H=16, W=24, C=64 if variant == _lib.VARIANT_MMA else 16, seed=81, depth="smooth")
     inp.nghbr_poses[0, 0, 2, 3] = -3.0            # z_src = z_ref - 3 < 0 for depths below 3 m
     inp.nghbr_poses[0, 1, 2, 3] = -2.4
     inp.nghbr_gmms[0, 1] = 1e6                    # view 0: consistency test wide open, so behind-camera samples count

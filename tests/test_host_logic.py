@@ -158,7 +158,7 @@ def test_packed_source_cache_hits_on_the_callers_tensor(monkeypatch):
     """the repack must be keyed on the tensor object the caller passes — a `.detach()` temporary dies
     before the next call and made every est_costvolume_CW call repack (157 MB at config 2).  Counted with mocked ops."""
     from magnet_b200 import homography as hg, ops
-    calls = {"pixc": 0, "tiled": 0}
+    calls = {"pixc": 0, "tiled": 0, "split": 0}
 
     def fake_pixc(x, gmm=None, out=None):
         calls["pixc"] += 1
@@ -168,27 +168,41 @@ def test_packed_source_cache_hits_on_the_callers_tensor(monkeypatch):
         calls["tiled"] += 1
         return torch.zeros(1)
 
+    def fake_split(x, gmm=None, out=None):
+        calls["split"] += 1
+        return torch.zeros(1, dtype=torch.uint8)
+
     monkeypatch.setattr(ops, "repack_pixc", fake_pixc)
     monkeypatch.setattr(ops, "repack_tiled32", fake_tiled)
+    monkeypatch.setattr(ops, "repack_split16", fake_split)
     hg.clear_cache()
     feat, gmm = torch.zeros(4, 16, 3, 5), torch.zeros(4, 2, 3, 5)
     for _ in range(3):                                       # the N_iter calls of one forward
-        _, layout = hg._packed_source(feat, gmm, 2, _lib.VARIANT_AUTO)
+        _, layout, _ = hg._packed_source(feat, gmm, 2, _lib.VARIANT_AUTO)
         assert layout == _lib.SRC_PIXC
     assert calls["pixc"] == 1
     feat.add_(1.0)                                           # next forward writes new features in place
     hg._packed_source(feat, gmm, 2, _lib.VARIANT_AUTO)
     assert calls["pixc"] == 2
     for _ in range(2):                                       # cross-check variants read TILED32, cached separately
-        _, layout = hg._packed_source(feat, gmm, 2, _lib.VARIANT_CELLS)
+        _, layout, _ = hg._packed_source(feat, gmm, 2, _lib.VARIANT_CELLS)
         assert layout == _lib.SRC_TILED32
     assert calls["tiled"] == 1
+    # C == 64: the tensor-core kernel's fp16 hi/lo planes, source views and reference features split once per forward
+    feat64, ref64 = torch.zeros(4, 64, 3, 5), torch.zeros(2, 64, 3, 5)
+    for _ in range(3):
+        _, layout, ref_split = hg._packed_source(feat64, gmm, 2, _lib.VARIANT_AUTO, ref64)
+        assert layout == _lib.SRC_SPLIT16 and ref_split is not None
+    assert calls["split"] == 2
+    ref64.add_(1.0)
+    hg._packed_source(feat64, gmm, 2, _lib.VARIANT_AUTO, ref64)
+    assert calls["split"] == 3                               # only the reference features changed
     hg.prep_cache(False)
     hg._packed_source(feat, gmm, 2, _lib.VARIANT_AUTO)
     hg._packed_source(feat, gmm, 2, _lib.VARIANT_AUTO)
     assert calls["pixc"] == 4                                # disabled: every call repacks
     hg.prep_cache(True)
-    _, layout = hg._packed_source(torch.zeros(4, 20, 3, 5), None, 2, _lib.VARIANT_AUTO)
+    _, layout, _ = hg._packed_source(torch.zeros(4, 20, 3, 5), None, 2, _lib.VARIANT_AUTO)
     assert layout == _lib.SRC_TILED32                        # C = 20: not a PIXC channel count
     hg.clear_cache()
 

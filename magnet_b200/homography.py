@@ -120,21 +120,26 @@ def _camera_table(cam_intrins, R, t, is_valid, device):
     return _cache.put("cams", src, ops.pack_cameras(intM_d, R, t, valid_d), extra)
 
 
-def _wants_split16(C: int, V: int, variant: int) -> bool:
-    return variant in (_lib.VARIANT_AUTO, _lib.VARIANT_MMA) and C == 64 and V <= 16
+MMA_MIN_PLANES = 32   # below half a 64-hypothesis chunk the all-pairs GEMM is wasted: the gather kernel is faster (profiles/r2_ship_point.md)
+
+
+def _wants_split16(C: int, V: int, variant: int, D: int) -> bool:
+    if variant == _lib.VARIANT_MMA:
+        return C == 64 and V <= 16
+    return variant == _lib.VARIANT_AUTO and C == 64 and V <= 16 and D >= MMA_MIN_PLANES
 
 
 def _wants_pixc(C: int, V: int, variant: int) -> bool:
     return variant in (_lib.VARIANT_AUTO, _lib.VARIANT_TMA) and C in (16, 32, 64) and V <= 16
 
 
-def _packed_source(nghbr_feat, nghbr_gmms, V, variant, ref_feat=None):
+def _packed_source(nghbr_feat, nghbr_gmms, V, variant, ref_feat=None, D=MMA_MIN_PLANES):
     """The source maps in the layout the selected kernel reads, repacked once per forward (cached on the caller's
     tensor objects): SPLIT16 (fp16 hi/lo planes + Gaussian table, also of the reference features) for the tensor-core
-    production kernel, PIXC (features + Gaussians, pixel-major) for the TMA-staged CUDA-core kernel, TILED32 for the
+    production kernel (C == 64 and at least MMA_MIN_PLANES hypotheses), PIXC (features + Gaussians, pixel-major) for the TMA-staged CUDA-core kernel, TILED32 for the
     global-gather kernels, NCHW when the channel count fits none.  Returns (source, layout, reference split or None)."""
     C = nghbr_feat.shape[1]
-    if _wants_split16(C, V, variant) and ref_feat is not None:
+    if _wants_split16(C, V, variant, D) and ref_feat is not None:
         src = (nghbr_feat,) if nghbr_gmms is None else (nghbr_feat, nghbr_gmms)
         hit = _cache.get("split16", src)
         if hit is None:
@@ -178,7 +183,7 @@ def est_costvolume_CW(d_volume, ref_feat, nghbr_feat, ref_gmms, nghbr_gmms,
     with torch.no_grad():
         _, rays_d = _device_intrinsics(cam_intrins, device)
         cams = _camera_table(cam_intrins, R, t, is_valid, device)
-        src, layout, ref_split = _packed_source(nghbr_feat, nghbr_gmms, V, variant, ref_feat)
+        src, layout, ref_split = _packed_source(nghbr_feat, nghbr_gmms, V, variant, ref_feat, int(d_volume.shape[1]))
         return ops.cost_volume(ref_feat.detach(), src, rays_d, cams, V=V, src_layout=layout, consistency=True,
                                src_gmm=nghbr_gmms.detach(), kappa=float(thres), d_volume=d_volume.detach(),
                                variant=variant, ref_split=ref_split)
@@ -198,7 +203,7 @@ class _CostVolumeF(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, ref_feat, nghbr_feat, planes, rays_d, cams, V, variant):
-        src, layout, ref_split = _packed_source(nghbr_feat, None, V, variant, ref_feat)
+        src, layout, ref_split = _packed_source(nghbr_feat, None, V, variant, ref_feat, len(planes))
         out = ops.cost_volume(ref_feat.detach(), src, rays_d, cams, V=V, src_layout=layout, consistency=False,
                               k=planes, planes=True, softmax=True, variant=variant, ref_split=ref_split)
         ctx.save_for_backward(ref_feat.detach(), nghbr_feat.detach(), out, rays_d, cams)

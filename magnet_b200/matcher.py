@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
+from .homography import MMA_MIN_PLANES
 from .sampling import depth_sampling
 
 
@@ -72,9 +73,10 @@ class MatchingPlan:
         self._nghbr_feat = nghbr_feat.detach()
         self._packed = {}
         self._ref_split = None
-        # Production: the tensor-core kernel on the fp16 hi/lo planes (C == 64); otherwise the global-gather kernel
-        # (TILED32), the faster CUDA-core one at every measured size (profiles/r2_kernels.md).  Pass
-        # src_layout=SRC_PIXC / variant=VARIANT_TMA for the TMA-staged CUDA-core kernel.
+        # Production: the tensor-core kernel on the fp16 hi/lo planes (C == 64 and at least half a chunk of hypotheses,
+        # decided per cost() call); otherwise the global-gather kernel (TILED32), the faster CUDA-core one at every
+        # measured size (profiles/r2_kernels.md).  Pass src_layout=SRC_PIXC / variant=VARIANT_TMA for the TMA-staged
+        # CUDA-core kernel.  Layouts are packed on first use.
         if src_layout == _lib.SRC_SPLIT16 and not (self.C == 64 and self.V <= 16):
             src_layout = _lib.SRC_TILED32
         if src_layout == _lib.SRC_PIXC and not (self.C in (16, 32, 64) and self.V <= 16):
@@ -82,7 +84,6 @@ class MatchingPlan:
         if src_layout == _lib.SRC_TILED32 and self.C % 4 != 0:
             src_layout = _lib.SRC_NCHW
         self.layout = src_layout
-        self.src = self._source(src_layout)
 
     def _source(self, layout: int):
         """Source maps in ``layout`` (built on first use; the cross-check variants read other layouts than production)."""
@@ -101,6 +102,9 @@ class MatchingPlan:
     def cost(self, gmm: torch.Tensor, k, out: Optional[torch.Tensor] = None, variant=_lib.VARIANT_AUTO):
         """Fused sampler + CW cost volume for the current Gaussian (B,2,H,W)."""
         layout = self.layout
+        n_planes = len(k)
+        if layout == _lib.SRC_SPLIT16 and variant == _lib.VARIANT_AUTO and n_planes < MMA_MIN_PLANES:
+            layout = _lib.SRC_TILED32 if self.C % 4 == 0 else _lib.SRC_NCHW   # few hypotheses: the gather kernel is faster
         if variant == _lib.VARIANT_TMA:
             layout = _lib.SRC_PIXC                         # the TMA-staged kernel fetches its windows from PIXC
         elif variant == _lib.VARIANT_MMA:

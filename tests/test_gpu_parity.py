@@ -147,9 +147,10 @@ def test_mma_kernel_fuzz_against_direct_kernel(cuda):
         k = inp.k.tolist()
         want = plan.cost(g.ref_gmms, k, variant=_lib.VARIANT_DIRECT)
         dvol = ops.sample_depths(g.ref_gmms, k)
-        for mode, got in (("fused", plan.cost(g.ref_gmms, k)),
+        for mode, got in (("fused", plan.cost(g.ref_gmms, k, variant=_lib.VARIANT_MMA)),
                           ("drop-in", magnet_b200.est_costvolume_CW(dvol, g.ref_feat, g.nghbr_feat, g.ref_gmms, g.nghbr_gmms,
-                                                                      g.R, g.t, inp.is_valid, inp.cam_intrins, inp.thres))):
+                                                                      g.R, g.t, inp.is_valid, inp.cam_intrins, inp.thres,
+                                                                      variant=_lib.VARIANT_MMA))):
             assert torch.isfinite(got).all(), (it, mode)
             sc = max(float(want.abs().max()), 1e-20)
             d = (got - want).abs()

@@ -191,16 +191,17 @@ def test_packed_source_cache_hits_on_the_callers_tensor(monkeypatch):
     # C == 64: the tensor-core kernel's fp16 hi/lo planes, source views and reference features split once per forward
     feat64, ref64 = torch.zeros(4, 64, 3, 5), torch.zeros(2, 64, 3, 5)
     for _ in range(3):
-        _, layout, ref_split = hg._packed_source(feat64, gmm, 2, _lib.VARIANT_AUTO, ref64)
+        _, layout, ref_split = hg._packed_source(feat64, gmm, 2, _lib.VARIANT_AUTO, ref64, 64)
         assert layout == _lib.SRC_SPLIT16 and ref_split is not None
     assert calls["split"] == 2
+    assert hg._packed_source(feat64, gmm, 2, _lib.VARIANT_AUTO, ref64, 5)[1] == _lib.SRC_PIXC   # N_s = 5: CUDA-core kernel
     ref64.add_(1.0)
-    hg._packed_source(feat64, gmm, 2, _lib.VARIANT_AUTO, ref64)
+    hg._packed_source(feat64, gmm, 2, _lib.VARIANT_AUTO, ref64, 64)
     assert calls["split"] == 3                               # only the reference features changed
     hg.prep_cache(False)
     hg._packed_source(feat, gmm, 2, _lib.VARIANT_AUTO)
     hg._packed_source(feat, gmm, 2, _lib.VARIANT_AUTO)
-    assert calls["pixc"] == 4                                # disabled: every call repacks
+    assert calls["pixc"] == 5                                # disabled: every call repacks
     hg.prep_cache(True)
     _, layout, _ = hg._packed_source(torch.zeros(4, 20, 3, 5), None, 2, _lib.VARIANT_AUTO)
     assert layout == _lib.SRC_TILED32                        # C = 20: not a PIXC channel count

@@ -527,10 +527,14 @@ __device__ __forceinline__ int split16_shift(unsigned absmax_bits) {
   return max(-100, min(100, 14 - (e - 127)));
 }
 
+// One CTA per SPX pixels of one image: channel planes are read coalesced along the pixels (16-byte loads when the image
+// size allows, all of a thread's loads in flight together), transposed through shared memory, and the two fp16 planes
+// are written as contiguous 128-byte pixel rows.
+template <int SPX, bool VEC>
 __global__ void __launch_bounds__(256) split16_repack_kernel(const float* __restrict__ src, const float* __restrict__ gmm,
                                                              unsigned char* __restrict__ dst, int N, int HW) {
   constexpr int C = 64;
-  __shared__ float t[32 * (C + 1)];
+  __shared__ float t[SPX * (C + 1)];
   Split16Header* hdr = reinterpret_cast<Split16Header*>(dst);
   const int sh = split16_shift(hdr->absmax);
   const float s = __uint_as_float((unsigned)(127 + sh) << 23);
@@ -538,28 +542,54 @@ __global__ void __launch_bounds__(256) split16_repack_kernel(const float* __rest
     hdr->scale = s;
     hdr->inv_scale = __uint_as_float((unsigned)(127 - sh) << 23);
   }
-  const int xi = threadIdx.x & 31, cy = threadIdx.x >> 5;
   const size_t img = blockIdx.y;
-  const int p0 = blockIdx.x * 32;
-  const int pix = p0 + xi;
-  for (int c = cy; c < C; c += 8) t[xi * (C + 1) + c] = pix < HW ? src[(img * C + c) * HW + pix] : 0.0f;
+  const int p0 = blockIdx.x * SPX;
+  if (VEC) {                                               // HW % 4 == 0, src 16-byte aligned
+    static_assert(SPX == 128, "thread mapping below");
+    constexpr int CPI = 8;                                 // channels per iteration
+    // a warp reads 4 channel rows x 8 float4 (4 x 128 contiguous bytes); this way its transposed stores hit 32 banks
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q4 = (warp & 3) * 8 + (lane & 7), c0 = (warp >> 2) * 4 + (lane >> 3);
+    float4 v[C / CPI];
+#pragma unroll
+    for (int e = 0; e < C / CPI; ++e) {
+      const int c = c0 + e * CPI, pix = p0 + 4 * q4;
+      v[e] = pix < HW ? __ldg(reinterpret_cast<const float4*>(src + (img * C + c) * HW + pix)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int e = 0; e < C / CPI; ++e) {
+      const int c = c0 + e * CPI;
+      t[(4 * q4 + 0) * (C + 1) + c] = v[e].x;
+      t[(4 * q4 + 1) * (C + 1) + c] = v[e].y;
+      t[(4 * q4 + 2) * (C + 1) + c] = v[e].z;
+      t[(4 * q4 + 3) * (C + 1) + c] = v[e].w;
+    }
+  } else {
+    const int xi = threadIdx.x % SPX, cy = threadIdx.x / SPX;
+    for (int c = cy; c < C; c += 256 / SPX) t[xi * (C + 1) + c] = p0 + xi < HW ? src[(img * C + c) * HW + p0 + xi] : 0.0f;
+  }
   __syncthreads();
   __half* planes = reinterpret_cast<__half*>(dst + SPLIT16_HEADER);
   float4* meta = reinterpret_cast<float4*>(dst + SPLIT16_HEADER + (size_t)N * HW * 256);
-  const int pl = threadIdx.x >> 3, q = threadIdx.x & 7;     // pixel of the group, 8-channel chunk
-  if (p0 + pl < HW) {
-    __align__(16) __half hi[8], lo[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float v = t[pl * (C + 1) + q * 8 + e] * s;
-      hi[e] = __float2half_rn(v);
-      lo[e] = __float2half_rn(v - __half2float(hi[e]));
+  for (int itw = 0; itw < SPX * 8 / 256; ++itw) {
+    const int item = itw * 256 + threadIdx.x;
+    const int pl = item >> 3, q = item & 7;                // pixel of the group, 8-channel chunk
+    if (p0 + pl < HW) {
+      __align__(16) __half hi[8], lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float v = t[pl * (C + 1) + q * 8 + e] * s;
+        hi[e] = __float2half_rn(v);
+        lo[e] = __float2half_rn(v - __half2float(hi[e]));
+      }
+      const size_t o = (size_t)(p0 + pl) * 64 + q * 8;
+      *reinterpret_cast<uint4*>(planes + (img * 2 + 0) * (size_t)HW * 64 + o) = *reinterpret_cast<const uint4*>(hi);
+      *reinterpret_cast<uint4*>(planes + (img * 2 + 1) * (size_t)HW * 64 + o) = *reinterpret_cast<const uint4*>(lo);
     }
-    const size_t o = (size_t)(p0 + pl) * 64 + q * 8;
-    *reinterpret_cast<uint4*>(planes + (img * 2 + 0) * (size_t)HW * 64 + o) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(planes + (img * 2 + 1) * (size_t)HW * 64 + o) = *reinterpret_cast<const uint4*>(lo);
   }
-  if (threadIdx.x < 32 && pix < HW) {
+  if (threadIdx.x < SPX && p0 + threadIdx.x < HW) {
+    const int pix = p0 + threadIdx.x;
     float mu = 0.0f, sg = 0.0f;
     if (gmm != nullptr) {
       mu = gmm[(img * 2 + 0) * HW + pix];
@@ -580,8 +610,14 @@ cudaError_t launch_repack_split16(const float* src, const float* gmm, void* dst,
   const int blocks = (int)std::min<size_t>(148 * 8, (n4 + 255) / 256 + 1);
   absmax_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(src), n4, src + n4 * 4, (int)(n - n4 * 4),
                                         reinterpret_cast<unsigned*>(static_cast<unsigned char*>(dst) + offsetof(Split16Header, absmax)));
-  dim3 grid((HW + 31) / 32, N), block(256);
-  split16_repack_kernel<<<grid, block, 0, st>>>(src, gmm, static_cast<unsigned char*>(dst), N, HW);
+  dim3 block(256);
+  if (HW % 4 == 0 && reinterpret_cast<uintptr_t>(src) % 16 == 0) {
+    dim3 grid((HW + 127) / 128, N);
+    split16_repack_kernel<128, true><<<grid, block, 0, st>>>(src, gmm, static_cast<unsigned char*>(dst), N, HW);
+  } else {
+    dim3 grid((HW + 31) / 32, N);
+    split16_repack_kernel<32, false><<<grid, block, 0, st>>>(src, gmm, static_cast<unsigned char*>(dst), N, HW);
+  }
   *launches = 2;
   return cudaGetLastError();
 }

@@ -25,7 +25,16 @@ METRICS = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 
            'smsp__warps_eligible.avg.per_cycle_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__cycles_active.avg']
 
 traffic = {"_source": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, ncu --set full (profiles/%s_ncu_*.md)" % name}
-for rep, title, key in (("cells_cfg2.ncu-rep", "cost_cells_kernel<64,GAUSS,CW> at cfg2 (fused sampler, TILED32 global gather) — the "
+try:                                                       # keep the entries of earlier visits (other kernels)
+    traffic.update({k: v for k, v in json.load(open(os.path.join(out, "traffic.json"))).items() if k != "_source"})
+except Exception:
+    pass
+for rep, title, key in (("mma_cfg2.ncu-rep", "cost_mma_kernel<GAUSS,CW> at cfg2 (fused sampler, SPLIT16 planes, tcgen05.mma + TMA "
+                         "windows) — the kernel bench.py's headline runs", "cfg2:mma"),
+                        ("mma_cfg3.ncu-rep", "cost_mma_kernel<GAUSS,CW> at cfg3 (KITTI shape)", "cfg3:mma"),
+                        ("mma_cfg2_volume.ncu-rep", "cost_mma_kernel<VOLUME,CW> at cfg2 (drop-in d_volume mode) — the kernel "
+                         "est_costvolume_CW runs", "cfg2:mma:dropin"),
+                        ("cells_cfg2.ncu-rep", "cost_cells_kernel<64,GAUSS,CW> at cfg2 (fused sampler, TILED32 global gather) — the "
                          "kernel bench.py's headline runs", "cfg2"),
                         ("cells_cfg3.ncu-rep", "cost_cells_kernel<64,GAUSS,CW> at cfg3 (KITTI shape)", "cfg3"),
                         ("tma_cfg2_volume.ncu-rep", "cost_tma_kernel<64,VOLUME,CW> at cfg2 (drop-in d_volume mode, PIXC + TMA window) — the "

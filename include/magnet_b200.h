@@ -55,7 +55,8 @@ typedef enum magnet_src_layout {
                             TMA-staged production kernel fetches its windows from.  With this layout
                             magnet_cost_args.src_gmm is ignored (the Gaussians travel inside src_feat). */
   MAGNET_SRC_SPLIT16 = 3  /* tensor-core layout (C == 64): a 256-byte header (power-of-two scale s), two fp16 planes
-                            (V*B, 2, H, W, 64) with x*s = hi + lo, and a (V*B, H, W, 4) table (mu, sigma, 0, 0); see
+                            (V*B, 2, H, W, 64) with x*s = hi + lo, and a (V*B, H, W+1, 4) table whose entry x+1 holds (mu, sigma) of
+                            pixel x and of pixel x+1 (zeros outside the row); see
                             magnet_repack_split16_f32 / magnet_split16_bytes.  With this layout ref_feat must ALSO
                             point to a split buffer (of the B reference feature maps, Gaussians NULL) and src_gmm is
                             ignored. */

@@ -52,13 +52,13 @@ constexpr int MSEG = 32;               // 8-cell segments per window: N <= 256 a
 constexpr int MMAXV = 16;              // views whose camera constants are staged in shared memory
 constexpr int M_TMEM_COLS = 256;
 constexpr int SEG_BYTES = 2048;        // hi atom (8 cells x 128 B) + lo atom
-constexpr int META_SEG_BYTES = 128;    // 8 cells x (mu, sigma, 0, 0)
+constexpr int META_SEG_BYTES = 128;    // 8 cells x (mu, sigma of the cell and of its right neighbour)
 
 // shared-memory map (bytes from the 1024-aligned base)
 constexpr int MOFF_A = 0;                                   // reference tile: hi 8 KB | lo 8 KB
 constexpr int MOFF_R = 16384;                               // window segments, later the accumulator rows G[64][GP]
 constexpr int MR_BYTES = 67584;                             //   >= 32 * 2048 and >= 64 * 260 * 4
-constexpr int MOFF_META = MOFF_R + MR_BYTES;                // float4[256] (mu, sigma, 0, 0) per window cell
+constexpr int MOFF_META = MOFF_R + MR_BYTES;                // float4[256] (mu, sigma)[c], (mu, sigma)[c + 1] per window cell
 constexpr int MOFF_CAM = MOFF_META + MSEG * META_SEG_BYTES; // magnet_camera[MMAXV]
 constexpr int MOFF_KS = MOFF_CAM + MMAXV * 64;              // float[MCH]
 constexpr int MOFF_BBOX = MOFF_KS + MCH * 4;                // int[2 slots][4]
@@ -78,7 +78,11 @@ struct Split16Header {
 };
 constexpr size_t SPLIT16_HEADER = 256;
 
-__host__ __device__ inline size_t split16_bytes(size_t N, size_t HW) { return SPLIT16_HEADER + N * HW * (256 + 16); }
+// header | fp16 planes (N, 2, H, W, 64) | table (N, H, W + 1, 4): entry x + 1 of a row = (mu, sigma)[x], (mu, sigma)[x + 1]
+// with zeros outside the row — both horizontal taps of a bilinear cell in ONE 16-byte read
+__host__ __device__ inline size_t split16_bytes(size_t N, size_t H, size_t W) {
+  return SPLIT16_HEADER + N * H * W * 256 + N * H * (W + 1) * 16;
+}
 
 __device__ __forceinline__ void mbar_wait_or_trap(uint32_t bar, uint32_t parity) {
   // bounded spin: a protocol error must surface as a launch failure, not as a hung GPU
@@ -110,14 +114,16 @@ __device__ __forceinline__ float lds_f32(uint32_t a) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
   return v;
 }
-__device__ __forceinline__ float2 lds_f32x2(uint32_t a) {
-  float2 v;
-  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+__device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
   return v;
 }
 // bilinear interpolation of a (mu, sigma) pair with packed f32x2 instructions; v01 - v00 as fma(v00, -1, v01) (exact
 // product, one rounding = the subtraction)
-__device__ __forceinline__ float2 lerp2d_x2(float2 v00, float2 v01, float2 v10, float2 v11, float fx, float fy) {
+__device__ __forceinline__ float2 lerp2d_x2(float4 top, float4 bot, float fx, float fy) {
+  const float2 v00 = make_float2(top.x, top.y), v01 = make_float2(top.z, top.w);
+  const float2 v10 = make_float2(bot.x, bot.y), v11 = make_float2(bot.z, bot.w);
   const float2 m1 = make_float2(-1.0f, -1.0f), fx2 = make_float2(fx, fx), fy2 = make_float2(fy, fy);
   const float2 t = __ffma2_rn(fx2, __ffma2_rn(v00, m1, v01), v00), u = __ffma2_rn(fx2, __ffma2_rn(v10, m1, v11), v10);
   return __ffma2_rn(fy2, __ffma2_rn(t, m1, u), t);
@@ -324,7 +330,7 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
           for (int s = warp; s < nsegs; s += MNT / 32) {
             const int r = s / nseg, xb = s - r * nseg;
             tma_load_5d(sbase + MOFF_R + (uint32_t)s * SEG_BYTES, &tm_src, bar_tma, 0, sx + 8 * xb, sy + r, 0, vb);
-            if (CW) tma_load_4d(m_base + (uint32_t)s * META_SEG_BYTES, &tm_meta, bar_tma, 0, sx + 8 * xb, sy + r, vb);
+            if (CW) tma_load_4d(m_base + (uint32_t)s * META_SEG_BYTES, &tm_meta, bar_tma, 0, sx + 8 * xb + 1, sy + r, vb);   // entry x + 1 <-> cell x
           }
         }
         __syncwarp();
@@ -423,8 +429,9 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
             bool oka, okb;
             if (CW) {
               const uint32_t ma = m_base + ca * 4u, mb = m_base + cb * 4u;
-              const float2 msa = lerp2d_x2(lds_f32x2(ma), lds_f32x2(ma + 16), lds_f32x2(ma + pitch4 * 4u), lds_f32x2(ma + pitch4 * 4u + 16), fx.x, fy.x);
-              const float2 msb = lerp2d_x2(lds_f32x2(mb), lds_f32x2(mb + 16), lds_f32x2(mb + pitch4 * 4u), lds_f32x2(mb + pitch4 * 4u + 16), fx.y, fy.y);
+              // table entry of a cell = (mu, sigma) of the cell and of its right neighbour: two 16-byte reads per hypothesis
+              const float2 msa = lerp2d_x2(lds_f32x4(ma), lds_f32x4(ma + pitch4 * 4u), fx.x, fy.x);
+              const float2 msb = lerp2d_x2(lds_f32x4(mb), lds_f32x4(mb + pitch4 * 4u), fx.y, fy.y);
               const float4 t2 = pixt[2 * i + 1];           // (q2, mu, sigma) of the pixel: broadcast
               const float2 dd = depth2(i, t2.y, t2.z);
               const float2 z = __fadd2_rn(make_float2(a2, a2), make_float2(__fmul_rn(t2.x, dd.x), __fmul_rn(t2.x, dd.y)));
@@ -498,7 +505,8 @@ cost_mma_kernel(const __grid_constant__ CostParams p, const __grid_constant__ CU
 
 // ---------------------------------------------------------------------------------------------------------------
 // MAGNET_SRC_SPLIT16 producer: (N, 64, H, W) fp32 [+ (N, 2, H, W) Gaussians] ->
-//   header | fp16 planes (N, 2, H, W, 64): hi = fp16(x*s), lo = fp16(x*s - hi) | table (N, H, W, 4) = (mu, sigma, 0, 0)
+//   header | fp16 planes (N, 2, H, W, 64): hi = fp16(x*s), lo = fp16(x*s - hi) | table (N, H, W + 1, 4), entry x + 1 =
+//   (mu[x], sigma[x], mu[x+1], sigma[x+1]), zeros outside the row
 // ---------------------------------------------------------------------------------------------------------------
 // bits of |x|, 0 for inf / NaN: the scale is chosen from the finite values, non-finite elements poison only their own
 // products
@@ -532,7 +540,7 @@ __device__ __forceinline__ int split16_shift(unsigned absmax_bits) {
 // are written as contiguous 128-byte pixel rows.
 template <int SPX, bool VEC>
 __global__ void __launch_bounds__(256) split16_repack_kernel(const float* __restrict__ src, const float* __restrict__ gmm,
-                                                             unsigned char* __restrict__ dst, int N, int HW) {
+                                                             unsigned char* __restrict__ dst, int N, int HW, int W) {
   constexpr int C = 64;
   __shared__ float t[SPX * (C + 1)];
   Split16Header* hdr = reinterpret_cast<Split16Header*>(dst);
@@ -544,7 +552,7 @@ __global__ void __launch_bounds__(256) split16_repack_kernel(const float* __rest
   }
   const size_t img = blockIdx.y;
   const int p0 = blockIdx.x * SPX;
-  if (VEC) {                                               // HW % 4 == 0, src 16-byte aligned
+  if constexpr (VEC) {                                     // HW % 4 == 0, src 16-byte aligned
     static_assert(SPX == 128, "thread mapping below");
     constexpr int CPI = 8;                                 // channels per iteration
     // a warp reads 4 channel rows x 8 float4 (4 x 128 contiguous bytes); this way its transposed stores hit 32 banks
@@ -588,14 +596,16 @@ __global__ void __launch_bounds__(256) split16_repack_kernel(const float* __rest
       *reinterpret_cast<uint4*>(planes + (img * 2 + 1) * (size_t)HW * 64 + o) = *reinterpret_cast<const uint4*>(lo);
     }
   }
-  if (threadIdx.x < SPX && p0 + threadIdx.x < HW) {
+  if (threadIdx.x < SPX && p0 + threadIdx.x < HW) {       // my (mu, sigma): first half of entry x + 1, second half of entry x
     const int pix = p0 + threadIdx.x;
-    float mu = 0.0f, sg = 0.0f;
-    if (gmm != nullptr) {
-      mu = gmm[(img * 2 + 0) * HW + pix];
-      sg = gmm[(img * 2 + 1) * HW + pix];
-    }
-    meta[img * HW + pix] = make_float4(mu, sg, 0.0f, 0.0f);
+    const int y = pix / W, x = pix - y * W;
+    float2 ms = make_float2(0.0f, 0.0f);
+    if (gmm != nullptr) ms = make_float2(gmm[(img * 2 + 0) * HW + pix], gmm[(img * 2 + 1) * HW + pix]);
+    float2* row = reinterpret_cast<float2*>(meta + (img * (HW / W) + y) * (size_t)(W + 1));
+    row[2 * (x + 1)] = ms;
+    row[2 * x + 1] = ms;
+    if (x == 0) row[0] = make_float2(0.0f, 0.0f);          // entry 0 = (outside, pixel 0)
+    if (x == W - 1) row[2 * W + 1] = make_float2(0.0f, 0.0f);   // entry W = (pixel W-1, outside)
   }
 }
 
@@ -613,10 +623,10 @@ cudaError_t launch_repack_split16(const float* src, const float* gmm, void* dst,
   dim3 block(256);
   if (HW % 4 == 0 && reinterpret_cast<uintptr_t>(src) % 16 == 0) {
     dim3 grid((HW + 127) / 128, N);
-    split16_repack_kernel<128, true><<<grid, block, 0, st>>>(src, gmm, static_cast<unsigned char*>(dst), N, HW);
+    split16_repack_kernel<128, true><<<grid, block, 0, st>>>(src, gmm, static_cast<unsigned char*>(dst), N, HW, W);
   } else {
     dim3 grid((HW + 31) / 32, N);
-    split16_repack_kernel<32, false><<<grid, block, 0, st>>>(src, gmm, static_cast<unsigned char*>(dst), N, HW);
+    split16_repack_kernel<32, false><<<grid, block, 0, st>>>(src, gmm, static_cast<unsigned char*>(dst), N, HW, W);
   }
   *launches = 2;
   return cudaGetLastError();
@@ -645,12 +655,12 @@ static cudaError_t make_planes_map(CUtensorMap* tm, const void* planes, int N, i
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-// rank-4 map over the (mu, sigma, 0, 0) table: (4 floats, W, H, N), box = 8 pixels of one row
+// rank-4 map over the paired (mu, sigma) table: (4 floats, W + 1, H, N), box = 8 entries of one row
 static cudaError_t make_meta_map(CUtensorMap* tm, const void* meta, int N, int H, int W) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return cudaErrorNotSupported;
-  const cuuint64_t dims[4] = {4, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  const cuuint64_t strides[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+  const cuuint64_t dims[4] = {4, (cuuint64_t)W + 1, (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t strides[3] = {16, ((cuuint64_t)W + 1) * 16, (cuuint64_t)H * (W + 1) * 16};
   const cuuint32_t box[4] = {4u, 8u, 1u, 1u};
   const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
   const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(meta), dims, strides, box, estr,
@@ -722,7 +732,7 @@ void mma_launch_info(int B, int H, int W, int D, int* grid, int* block, int* sme
   *smem = M_SMEM_TOTAL;
 }
 
-size_t split16_buffer_bytes(int N, int H, int W) { return split16_bytes((size_t)N, (size_t)H * W); }
+size_t split16_buffer_bytes(int N, int H, int W) { return split16_bytes((size_t)N, (size_t)H, (size_t)W); }
 
 cudaError_t launch_cost_mma(const CostParams& p, int mode, bool cw, cudaStream_t st) {
   if (cw) {

@@ -25,8 +25,11 @@ def check_split(x, gmm=None):
     print(f"  split16: scale {s:g} inv {inv:g} s*inv {s*inv:g} absmax {float(x.abs().max()):.4f} scaled max {float(x.abs().max())*s:.1f} "
           f"reconstruction max err / max {float(err):.3g}")
     if gmm is not None:
-        meta = buf[256 + N * H * W * 256:].view(torch.float32).view(N, H, W, 4)
-        print("  table ok:", bool(torch.equal(meta[..., 0], gmm[:, 0]) and torch.equal(meta[..., 1], gmm[:, 1]) and float(meta[..., 2:].abs().max()) == 0))
+        meta = buf[256 + N * H * W * 256:].view(torch.float32).view(N, H, W + 1, 4)
+        pad = torch.nn.functional.pad(gmm, (1, 1))           # (N,2,H,W+2): zeros left and right
+        ok = (torch.equal(meta[..., 0], pad[:, 0, :, :-1]) and torch.equal(meta[..., 1], pad[:, 1, :, :-1])
+              and torch.equal(meta[..., 2], pad[:, 0, :, 1:]) and torch.equal(meta[..., 3], pad[:, 1, :, 1:]))
+        print("  table ok:", bool(ok))
     return buf
 
 

@@ -8,7 +8,7 @@ for tool in memcheck racecheck synccheck; do
   timeout 900 compute-sanitizer --tool $tool --error-exitcode 7 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/$tool.log 2>&1
   echo "$tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|smoke ok" $OUT/$tool.log | tail -3
 done
-timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests -m gpu -q -x -k "golden or seeded or behind or known_answers or graph or non_finite or fused_upsample or camera_prep" > $OUT/memcheck_tests.log 2>&1; echo "memcheck tests rc=$?"; grep -E "ERROR SUMMARY|passed|failed" $OUT/memcheck_tests.log | tail -3
+timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests -m gpu -q -x -k "golden or seeded or behind or known_answers or graph or non_finite or fused_upsample or camera_prep or mma" > $OUT/memcheck_tests.log 2>&1; echo "memcheck tests rc=$?"; grep -E "ERROR SUMMARY|passed|failed" $OUT/memcheck_tests.log | tail -3
 echo "== bench"; timeout 900 python bench.py > "$OUT/bench.json" 2> "$OUT/bench.err"; echo "bench rc=$?"; tail -2 "$OUT/bench.err"
 python - "$OUT/bench.json" <<'PY'
 import json,sys

@@ -63,10 +63,13 @@ def main():
     reducer.broadcast_parameters(0)
     opt = torch.optim.AdamW(head.parameters(), lr=3.57e-4, weight_decay=1e-2)
 
-    losses, t0 = [], None
-    for step in range(args.steps + 2):
-        if step == 2:
+    WARM = 5                                                               # cuDNN autotuning, NCCL lazy init, allocator growth
+    losses, t0, marks = [], None, []
+    for step in range(args.steps + WARM):
+        if step == WARM:
             torch.cuda.synchronize(); md.barrier(); t0 = time.perf_counter()
+        if step >= WARM:
+            ev = torch.cuda.Event(enable_timing=True); ev.record(); marks.append(ev)
         if args.unfused_loss:
             preds = head(inp.ref_feat, inp.nghbr_feat, inp.ref_gmms, inp.nghbr_gmms, x_d3, inp.nghbr_poses,
                          inp.is_valid, inp.cam_intrins)
@@ -81,12 +84,15 @@ def main():
         torch.nn.utils.clip_grad_norm_(head.parameters(), 1.0)
         opt.step()
         losses.append(md.sum_over_ranks(float(loss.detach()), device=dev) / world)
+    ev = torch.cuda.Event(enable_timing=True); ev.record(); marks.append(ev)
     torch.cuda.synchronize(); md.barrier()
     dt = time.perf_counter() - t0
+    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(len(marks) - 1))   # device time between step starts
     if rank == 0:
         print(json.dumps({"config": "train head, ScanNet shape", "n_gpus": world, "global_batch": gb, "steps": args.steps,
                           "loss_path": "unfused (torch NLL on upsampled predictions)" if args.unfused_loss else "fused upsample+NLL kernels",
                           "ms_per_step": 1e3 * dt / args.steps, "frames_per_s": gb * args.steps / dt,
+                          "rank0_step_ms_median": per_step[len(per_step) // 2], "rank0_step_ms_max": per_step[-1],
                           "loss_first": losses[0], "loss_last": losses[-1], "trainable_params": reducer.bucket.numel()}))
     md.shutdown()
 

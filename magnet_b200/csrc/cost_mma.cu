@@ -9,24 +9,29 @@
 // products of ALL (reference pixel, window cell) pairs of an 8x8 tile are one small GEMM,
 //        G[p][c] = <ref_p, src_c>,  64 pixels x (<= 256 window cells) x 64 channels,
 // ~12x more products than needed but on the tensor pipe, which is otherwise idle; what remains per hypothesis is the
-// projection, four G[p][c] + four (mu, sigma)[c] shared-memory reads and three bilinear interpolations.
+// projection, four G[p][c] and two paired (mu, sigma) shared-memory reads and three bilinear interpolations.
 //
 //   * fp32 accuracy on fp16 tensor cores: every feature map is split once per forward into x*s = hi + lo (two fp16
-//     planes, s a power of two that maps max|x| into [2^14, 2^15)); hi*hi + hi*lo + lo*hi carries 22 significant bits
-//     per factor, products are exact in the fp32 accumulator (MAGNET_SRC_SPLIT16, magnet_repack_split16_f32).
-//   * the planes are (image, plane, y, x, 64 channels) fp16 = 128-byte rows: an 8-pixel TMA box with
+//     planes, s a power of two that maps the largest finite |x| into [2^14, 2^15)); hi*hi + hi*lo + lo*hi carries 22
+//     significant bits per factor, products are exact in the fp32 accumulator (MAGNET_SRC_SPLIT16,
+//     magnet_repack_split16_f32).
+//   * the planes are (image, plane, y, x, 64 channels) fp16 = 128-byte rows: an 8-pixel x 2-plane TMA box with
 //     CU_TENSOR_MAP_SWIZZLE_128B lands as one canonical K-major UMMA atom per plane; the window of a (tile, view) is the
 //     bounding box of the tile's sample positions cut into such 8-cell segments (zero fill outside the image =
 //     grid_sample's padding_mode='zeros'), cell index = B-operand row = accumulator column.  The reference tile is the
 //     A operand (rows 0..63 of an M = 128 instruction; rows 64..127 read whatever follows and are never looked at).
-//   * one warp per reference pixel, one LANE per hypothesis (two hypotheses per lane for a 64-hypothesis chunk): the
-//     pixel's constants are warp-uniform, the 32 lanes read a handful of neighbouring cells of ONE accumulator row
-//     (broadcast / conflict-free), the accumulators over the views stay in registers.
-//   * per view: project all hypotheses (bounding box per 32-hypothesis block) -> TMA window + (mu, sigma) table ->
-//     12 x tcgen05.mma (3 products x 4 K steps) -> tcgen05.ld the 64 accumulator rows into shared memory (over the
-//     window, which is dead by then) -> per-hypothesis phase.  Two CTAs per SM overlap each other's copy / MMA latency.
-//     A window that does not fit 256 cells is split into its two 32-hypothesis blocks; a block that still does not fit
-//     (incoherent depths) takes its taps from global memory, one hypothesis at a time across the warp.  Always correct.
+//   * one warp per tile row (8 pixels in turn), one LANE per hypothesis (lane j: hypotheses j and j + 32 of the
+//     64-hypothesis chunk, packed f32x2 arithmetic across the two): the pixel's constants are warp-uniform (per-warp table
+//     in shared memory), the 32 lanes read a handful of neighbouring cells of ONE accumulator row (broadcast /
+//     conflict-free); lanes beyond the last hypothesis replicate it, so there are no activity predicates.
+//   * per view: project all hypotheses (positions cached in registers, exact bounding box) -> TMA window + paired
+//     (mu, sigma) table -> 12 x tcgen05.mma (3 products x 4 K steps) committed to an mbarrier -> tcgen05.ld the 64
+//     accumulator rows into shared memory (over the window, which is dead by then) -> per-hypothesis phase.  The view
+//     accumulators live in shared memory (hypothesis-major: the layout the coalesced epilogue reads).
+//   * a window that does not fit 256 cells is cut into sub-windows of <= 32 segments that overlap by one cell column /
+//     row; a hypothesis is evaluated in the sub-window that holds its cell origin.  Same code for any depth distribution.
+//   * persistent CTAs (two per SM): work items (batch element, tile, 64-hypothesis chunk) come from a global counter in a
+//     per-launch slot that the last CTA re-arms (graph-replay safe); barriers and tensor memory are set up once per CTA.
 //
 // Numerics: the per-view channel sum is the tensor core's fp32 accumulation of exact products of the split factors
 // (relative error ~2^-21 of sum |ref||src|, the same order as an fp32 FMA chain); everything else — projection, weights,

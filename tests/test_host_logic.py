@@ -78,6 +78,34 @@ def test_launch_info_matches_design():
     assert (grid, block, smem) == (150 * 64 * 8, 128, 0)
 
 
+def test_split16_entry_points_without_gpu():
+    """MAGNET_SRC_SPLIT16 (tensor-core kernel): buffer size formula, argument validation, launch geometry — no compute calls."""
+    from magnet_b200 import ops
+    L = _lib.lib()
+    # header + fp16 hi/lo planes (N,2,H,W,64) + paired (mu, sigma) table (N,H,W+1,4)
+    assert L.magnet_split16_bytes(2, 3, 5) == 256 + 2 * 3 * 5 * 256 + 2 * 3 * 6 * 16
+    assert L.magnet_split16_bytes(0, 3, 5) == 0
+    buf = (C.c_float * 64)()
+    p = C.cast(buf, C.c_void_p)
+    assert L.magnet_repack_split16_f32(None, None, p, 1, 64, 2, 2, None) == _lib.ERR_NULL
+    assert L.magnet_repack_split16_f32(p, None, p, 1, 32, 2, 2, None) == _lib.ERR_UNSUPPORTED      # C == 64 only
+    assert L.magnet_repack_split16_f32(p, None, C.c_void_p(C.addressof(buf) + 4), 1, 64, 2, 2, None) == _lib.ERR_ALIGN
+    a = CostArgs()
+    a.B, a.V, a.D, a.C, a.H, a.W = 1, 2, 64, 32, 8, 8
+    a.ref_feat = a.src_feat = a.rays = a.cams = a.out = a.k_host = p
+    a.depth_mode, a.src_layout = _lib.DEPTH_PLANES, _lib.SRC_SPLIT16
+    assert L.magnet_cost_volume_f32(C.byref(a), None) == _lib.ERR_UNSUPPORTED                     # C == 64 only
+    a.C, a.variant = 64, _lib.VARIANT_CELLS
+    assert L.magnet_cost_volume_f32(C.byref(a), None) == _lib.ERR_UNSUPPORTED                     # SPLIT16 is read by the MMA kernel only
+    a.variant, a.src_layout = _lib.VARIANT_MMA, _lib.SRC_TILED32
+    assert L.magnet_cost_volume_f32(C.byref(a), None) == _lib.ERR_UNSUPPORTED                     # and the MMA kernel reads nothing else
+    grid, block, smem = ops.cost_launch_info(8, 4, 64, 64, 120, 160, variant=_lib.VARIANT_MMA)
+    assert block == 256 and grid <= 8 * 15 * 20 and grid % 2 == 0      # persistent: two CTAs per SM (or one per work item)
+    assert 2 * (smem + 1024) <= 227 * 1024                              # two CTAs per SM fit
+    with pytest.raises(_lib.MagnetError):
+        ops.repack_split16(torch.zeros(1, 64, 2, 2))                    # CPU tensor
+
+
 def test_ops_refuse_cpu_tensors():
     from magnet_b200 import ops
     x = torch.zeros(1, 2, 4, 4)

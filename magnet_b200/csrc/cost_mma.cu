@@ -108,7 +108,8 @@ __device__ __forceinline__ float lerp2d(float v00, float v01, float v10, float v
 }
 
 // work counters of the persistent kernel: one slot per launch in flight (host ticket), re-armed by the last CTA of the
-// launch, so a captured launch can be replayed.  Launches that share a slot must not run concurrently.
+// launch, so a captured launch can be replayed.  Launches that share a slot must not run concurrently: 512 eager
+// launches or 512 captured ones would have to be in flight / alive at once.
 constexpr int MMA_SLOTS = 1024;
 __device__ unsigned g_mma_next[MMA_SLOTS];
 __device__ unsigned g_mma_done[MMA_SLOTS];
@@ -714,8 +715,14 @@ static cudaError_t launch_mma_mw(const CostParams& p, cudaStream_t st) {
   const int nchunks = (p.D + MCH - 1) / MCH;
   const int tiles = ((p.W + MTW - 1) / MTW) * ((p.H + MTH - 1) / MTH);
   const int n_items = tiles * nchunks * p.B;
-  static std::atomic<unsigned> ticket{0};
-  const int slot = (int)(ticket.fetch_add(1) % MMA_SLOTS);
+  // work-counter slot of this launch: eager launches cycle through the lower half, launches recorded into a CUDA graph
+  // take theirs from the upper half (a replay reuses its slot for the life of the graph, so it must never meet an eager
+  // launch on another stream)
+  static std::atomic<unsigned> ticket{0}, graph_ticket{0};
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) cap = cudaStreamCaptureStatusNone;
+  const int slot = cap == cudaStreamCaptureStatusActive ? MMA_SLOTS / 2 + (int)(graph_ticket.fetch_add(1) % (MMA_SLOTS / 2))
+                                                        : (int)(ticket.fetch_add(1) % (MMA_SLOTS / 2));
   dim3 grid(std::min(n_items, 2 * sm_count(dev))), block(MNT);   // persistent: two CTAs per SM
   float* dbg = nullptr;
 #ifdef MAGNET_MMA_DEBUG

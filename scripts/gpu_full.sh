@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > "$OUT/gpu.txt
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/smoke.log" 2>&1; echo "smoke rc=$?"; tail -6 "$OUT/smoke.log"
 echo "== pytest"; timeout 1800 python -m pytest tests -m gpu -q > "$OUT/pytest.log" 2>&1; echo "pytest rc=$?"; tail -25 "$OUT/pytest.log" | cut -c1-250
 echo "== kbench"
-for a in "cfg2 mma 20 gauss" "cfg2 cells 20 gauss" "cfg2 tma 20 gauss" "cfg2 mma 20 volume" "cfg2 tma 20 volume" "cfg3 mma 20 gauss" "cfg3 cells 20 gauss" "cfg3 mma 20 volume"; do timeout 300 python scripts/kbench.py $a 2>&1 | tail -1; done | tee "$OUT/kbench.txt"
+for a in ${KB:-"cfg2 mma 20 gauss" "cfg2 cells 20 gauss" "cfg2 tma 20 gauss" "cfg2 mma 20 volume" "cfg2 tma 20 volume" "cfg3 mma 20 gauss" "cfg3 cells 20 gauss" "cfg3 mma 20 volume"}; do timeout 300 python scripts/kbench.py $a 2>&1 | tail -1; done | tee "$OUT/kbench.txt"
 echo "== bench"; timeout 900 python bench.py > "$OUT/bench.json" 2> "$OUT/bench.err"; echo "bench rc=$?"; tail -3 "$OUT/bench.err"
 python - "$OUT/bench.json" <<'PY'
 import json,sys

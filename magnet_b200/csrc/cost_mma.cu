@@ -102,11 +102,6 @@ __device__ __forceinline__ void mbar_wait_or_trap(uint32_t bar, uint32_t parity)
   __trap();
 }
 
-__device__ __forceinline__ float lerp2d(float v00, float v01, float v10, float v11, float fx, float fy) {
-  const float t = __fmaf_rn(fx, v01 - v00, v00), u = __fmaf_rn(fx, v11 - v10, v10);
-  return __fmaf_rn(fy, u - t, t);
-}
-
 // work counters of the persistent kernel: one slot per launch in flight (host ticket), re-armed by the last CTA of the
 // launch, so a captured launch can be replayed.  Launches that share a slot must not run concurrently: 512 eager
 // launches or 512 captured ones would have to be in flight / alive at once.

@@ -52,7 +52,7 @@ typedef enum magnet_src_layout {
                             contiguous (see magnet_repack_tiled32_f32).  Pixels x >= W are padding. */
   MAGNET_SRC_PIXC = 2,    /* (V*B, H, W, C+4): pixel-major, per pixel the C channels followed by the source
                             Gaussian (mu, sigma) and two zeros (see magnet_repack_pixc_f32): the layout the
-                            TMA-staged production kernel fetches its windows from.  With this layout
+                            TMA-staged CUDA-core kernel fetches its windows from.  With this layout
                             magnet_cost_args.src_gmm is ignored (the Gaussians travel inside src_feat). */
   MAGNET_SRC_SPLIT16 = 3  /* tensor-core layout (C == 64): a 256-byte header (power-of-two scale s), two fp16 planes
                             (V*B, 2, H, W, 64) with x*s = hi + lo, and a (V*B, H, W+1, 4) table whose entry x+1 holds (mu, sigma) of
@@ -71,7 +71,7 @@ typedef enum magnet_variant {
   MAGNET_VARIANT_CELLS = 2,  /* tap-sharing kernel: per-lane bilinear-cell records             */
   MAGNET_VARIANT_CELLS_NOREUSE = 3, /* diagnostic: as CELLS, but every cell gathers all 4 taps
                                        (MAGNET_DEPTH_GAUSS only)                               */
-  MAGNET_VARIANT_TMA = 4,    /* production: tap-sharing kernel, 4 lanes per pixel, the CTA's source window
+  MAGNET_VARIANT_TMA = 4,    /* CUDA-core tap-sharing kernel, 4 lanes per pixel, the CTA's source window
                                 staged in shared memory by TMA (MAGNET_SRC_PIXC only)          */
   MAGNET_VARIANT_MMA = 5     /* tensor-core kernel: all (reference pixel, window cell) channel dot products of an
                                 8x8 tile by tcgen05.mma into tensor memory (MAGNET_SRC_SPLIT16 only) */

@@ -1,4 +1,5 @@
-// MAGNET_VARIANT_TMA — production kernel of round 2: tap-sharing fused warp + sample + consistency + view fusion
+// MAGNET_VARIANT_TMA — TMA-staged CUDA-core kernel (MAGNET_SRC_PIXC; AUTO uses it for the drop-in path with few
+// hypotheses or C in {16, 32} — cost_mma.cu is the production kernel for C == 64): tap-sharing fused warp + sample + consistency + view fusion
 // with the CTA's source window staged in shared memory by TMA (cp.async.bulk.tensor, mbarrier completion) and the
 // per-hypothesis state held in tensor memory.
 //

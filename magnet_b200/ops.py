@@ -95,7 +95,7 @@ def repack_tiled32(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch
 
 def repack_pixc(x: torch.Tensor, gmm: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """(N,C,H,W) features [+ (N,2,H,W) Gaussians] -> PIXC (N, H, W, C+4): pixel-major, per pixel the C channels then
-    (mu, sigma, 0, 0) — the layout the TMA-staged production kernel fetches its windows from.  C in {16, 32, 64}."""
+    (mu, sigma, 0, 0) — the layout the TMA-staged CUDA-core kernel fetches its windows from.  C in {16, 32, 64}."""
     x = _need_cuda_f32("x", x)
     N, Cc, H, W = x.shape
     gptr = None
